@@ -1,0 +1,148 @@
+/* kdpt.h — C ABI of the B200-native KD-tree traversal / path-tracing hot path.
+ *
+ * Drop-in boundary for the render-loop interface of reddeupenn/kdtreePathTracerOptimization:
+ *     void pathtraceInit(Scene*, bool enablekd);                       src/pathtrace.h:6   (pathtrace.cu:201-272)
+ *     void pathtraceFree(Scene*, bool enablekd);                       src/pathtrace.h:7   (pathtrace.cu:274-313)
+ *     void pathtrace(uchar4* pbo, int frame, int iteration, ...);      src/pathtrace.h:8-21 (pathtrace.cu:2405-2635)
+ * The reference passes a C++ `Scene*`; this ABI takes exactly the flat arrays pathtraceInit reads from it
+ * (pathtrace.cu:203-258) with the reference's own POD layouts, so a maintainer binds it with a 20-line shim
+ * (INTEGRATION.md). Plain pointers and sizes only; no C++ or torch types.
+ *
+ * All functions return 0 on success and a negative kdpt_status otherwise; kdpt_last_error() gives the message of
+ * the calling thread's last failure. Nothing here ever calls exit() (the reference's checkCUDAError does,
+ * pathtrace.cu:38-60). There is no CPU fallback: without a usable CUDA device every entry point fails with
+ * KDPT_ERR_CUDA.
+ */
+#ifndef KDPT_H
+#define KDPT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDPT_ABI_VERSION 1
+
+typedef enum {
+    KDPT_OK = 0,
+    KDPT_ERR_ARG = -1,     /* bad argument / malformed tree */
+    KDPT_ERR_CUDA = -2,    /* CUDA runtime error or no device */
+    KDPT_ERR_ALLOC = -3,
+    KDPT_ERR_STATE = -4    /* call not valid for this context (e.g. render without camera) */
+} kdpt_status;
+
+/* ---- reference POD layouts, accepted verbatim (x86-64 sizeof/offsetof as in SURVEY.md §8b) ------------------ */
+typedef struct {            /* KDN::NodeBare, src/KDnode.h:64-82 — 64 B */
+    int axis; float splitPos; float mins[3]; float maxs[3];
+    int ID, parentID, leftID, rightID; int triIdStart, triIdSize; float tmin, tmax;
+} kdpt_node_bare;
+
+typedef struct {            /* KDN::TriBare, src/KDnode.h:51-62 — 76 B, component-major */
+    float x1, x2, x3, y1, y2, y3, z1, z2, z3;
+    float nx1, nx2, nx3, ny1, ny2, ny3, nz1, nz2, nz3;
+    int mtlIdx;
+} kdpt_tri_bare;
+
+typedef struct {            /* Geom, src/sceneStructs.h:22-31 — 236 B; mat4 are column-major (glm) */
+    int type;               /* 0 = SPHERE, 1 = CUBE (src/sceneStructs.h:10-13) */
+    int materialid;
+    float translation[3], rotation[3], scale[3];
+    float transform[16], inverseTransform[16], invTranspose[16];
+} kdpt_geom;
+
+typedef struct {            /* Material, src/sceneStructs.h:33-44 — 56 B */
+    float color[3]; float specular_exponent; float specular_color[3];
+    float hasReflective, hasRefractive, indexOfRefraction, emittance; float transmittance[3];
+} kdpt_material;
+
+typedef struct {            /* Camera, src/sceneStructs.h:46-55 — 84 B */
+    int resolution[2]; float position[3], lookAt[3], view[3], up[3], right[3], fov[2], pixelLength[2];
+} kdpt_camera;
+
+/* What pathtraceInit(Scene*) reads (pathtrace.cu:203-258): hst_scene->geoms, materials, newNodesBare/numNodes,
+ * newTrianglesBare/numTriangles, obj_materialOffsets/obj_numshapes, state.camera, state.traceDepth. */
+typedef struct {
+    const kdpt_node_bare* nodes; int numNodes;
+    const kdpt_tri_bare* tris; int numTris;
+    const kdpt_geom* geoms; int numGeoms;
+    const kdpt_material* materials; int numMaterials;
+    const int* objMaterialOffsets; int numShapes;
+    kdpt_camera camera;
+    int traceDepth;
+} kdpt_scene;
+
+/* ---- traversal-only entry point (what the reference's pathTraceOneBounceKDbare does per ray, minus scatter) -- */
+typedef struct { float origin[3]; float direction[3]; } kdpt_ray;          /* 24 B */
+
+typedef struct {            /* 32 B */
+    float t;                /* the reference's t_min: |o - (o + d*z + n*eps)|, or the incoming t_min when no hit */
+    float z, u, v;          /* glm::intersectRayTriangle baryPosition .z / .x / .y of the accepted triangle */
+    int tri;                /* canonical TriBare index (first entry with identical 76 bytes) or -1 */
+    float normal[3];        /* normalised interpolated normal of the accepted triangle */
+} kdpt_hit;
+
+typedef enum {
+    /* exact closest hit (== brute force over TriBare[] with the reference's arithmetic and acceptance rule) */
+    KDPT_FULLSTACK = 0,     /* near-first traversal, full per-ray stack; nudge 1e-5 (traverseKDbare's) */
+    KDPT_SHORTSTACK = 1,    /* short register stack + restart;           nudge 1e-4 (traverseKDbareShortHybrid's) */
+    /* bit-compatible with the reference's own (lossy) functions, including the hits they drop */
+    KDPT_REF_T1 = 2,        /* traverseKDbare,            pathtrace.cu:881-1020 */
+    KDPT_REF_T2 = 3,        /* traverseKDbareShortHybrid, pathtrace.cu:1023-1235 */
+    KDPT_MODE_COUNT = 4
+} kdpt_mode;
+
+/* ---- render loop toggles: the trailing arguments of pathtrace(), src/pathtrace.h:8-21, defaults main.cpp:35-60 */
+typedef struct {
+    float focalLength;      /* dofDistance, default 6 */
+    float dofAngle;         /* default 0 */
+    float softness;         /* default 0 */
+    int antialias;          /* default 1 */
+    int enableSss;          /* default 0 */
+    int compaction;         /* default 1 */
+    int mode;               /* kdpt_mode; the reference's SHORTSTACK=true is KDPT_REF_T2, false KDPT_REF_T1 */
+    int sortByMaterial;     /* 0 never, 1 only in iteration 2 (reference, pathtrace.cu:2600), 2 every bounce */
+    int reserved[4];
+} kdpt_params;
+
+typedef struct {            /* filled by kdpt_render */
+    uint64_t rayBounces;    /* paths traced summed over bounces and iterations */
+    uint64_t launches;      /* kernels launched */
+    float intersectMs;      /* device time of the intersect kernels (the reference's TESTINGMODE number) */
+    float totalMs;          /* device time of the whole call */
+} kdpt_render_stats;
+
+typedef struct kdpt_ctx kdpt_ctx;
+
+int kdpt_abi_version(void);
+const char* kdpt_last_error(void);
+
+/* pathtraceInit: flatten + upload. device = CUDA ordinal. The host arrays are not retained. */
+int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out);
+/* pathtraceFree */
+int kdpt_destroy(kdpt_ctx* ctx);
+
+/* sizes of the flattened device representation (bytes), for roofline bookkeeping */
+int kdpt_tree_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* maxDepth, int* maxLeaf,
+                   uint64_t* deviceBytes);
+
+/* n rays in, n hits out, HOST buffers (H2D + kernel + D2H). t_min_in may be NULL (FLT_MAX). */
+int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n, kdpt_hit* hits, int mode);
+/* same with DEVICE buffers on ctx's device; asynchronous on `stream` (a cudaStream_t, NULL = ctx's own stream,
+ * in which case the call returns after the kernel has been enqueued; use kdpt_sync). */
+int kdpt_trace_device(kdpt_ctx* ctx, const kdpt_ray* d_rays, const float* d_t_min_in, int n, kdpt_hit* d_hits,
+                      int mode, void* stream);
+int kdpt_sync(kdpt_ctx* ctx);
+
+/* pathtrace(): iterations iter_begin .. iter_begin+iter_count-1 (the reference counts from 1), accumulating into
+ * the context's radiance buffer. iter_stride > 1 renders iter_begin, iter_begin+stride, ... (sample sharding). */
+int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, const kdpt_params* params,
+                kdpt_render_stats* stats);
+int kdpt_clear_image(kdpt_ctx* ctx);
+/* accumulated radiance, W*H*3 floats (scene->state.image, pathtrace.cu:2631) */
+int kdpt_get_image(kdpt_ctx* ctx, float* rgb);
+/* device pointer of that buffer (for an NCCL all-reduce issued by the caller) */
+int kdpt_image_device(kdpt_ctx* ctx, float** d_rgb, int* numFloats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,236 @@
+"""kdtreepathtraceroptimization_b200 — host-side mirror (Python, ctypes) of the C ABI in include/kdpt.h.
+
+The product is the shared library ``libkdpt.so`` next to this file (hand-written sm_100a kernels behind a C ABI that
+replaces the reference's ``pathtraceInit / pathtrace / pathtraceFree``, src/pathtrace.h:6-21). This module only binds
+it for the tests and the benchmark: numpy dtypes of the reference's POD structs, a ``Context`` object and helpers to
+load a flattened scene. There is no CPU implementation here: if the library is missing or no CUDA device is usable,
+every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkdpt.so")
+
+# ---- reference POD layouts (sizes asserted against the library's static_asserts via kdpt_abi_version) -----------
+NODE = np.dtype([('axis', 'i4'), ('splitPos', 'f4'), ('mins', 'f4', 3), ('maxs', 'f4', 3), ('ID', 'i4'), ('parentID', 'i4'),
+                 ('leftID', 'i4'), ('rightID', 'i4'), ('triIdStart', 'i4'), ('triIdSize', 'i4'), ('tmin', 'f4'), ('tmax', 'f4')])
+TRI = np.dtype([(k, 'f4') for k in "x1 x2 x3 y1 y2 y3 z1 z2 z3 nx1 nx2 nx3 ny1 ny2 ny3 nz1 nz2 nz3".split()] + [('mtlIdx', 'i4')])
+GEOM = np.dtype([('type', 'i4'), ('materialid', 'i4'), ('translation', 'f4', 3), ('rotation', 'f4', 3), ('scale', 'f4', 3),
+                 ('transform', 'f4', 16), ('inverseTransform', 'f4', 16), ('invTranspose', 'f4', 16)])
+MATERIAL = np.dtype([('color', 'f4', 3), ('specular_exponent', 'f4'), ('specular_color', 'f4', 3), ('hasReflective', 'f4'),
+                     ('hasRefractive', 'f4'), ('indexOfRefraction', 'f4'), ('emittance', 'f4'), ('transmittance', 'f4', 3)])
+CAMERA = np.dtype([('resolution', 'i4', 2), ('position', 'f4', 3), ('lookAt', 'f4', 3), ('view', 'f4', 3), ('up', 'f4', 3),
+                   ('right', 'f4', 3), ('fov', 'f4', 2), ('pixelLength', 'f4', 2)])
+RAY = np.dtype([('origin', 'f4', 3), ('direction', 'f4', 3)])
+HIT = np.dtype([('t', 'f4'), ('z', 'f4'), ('u', 'f4'), ('v', 'f4'), ('tri', 'i4'), ('normal', 'f4', 3)])
+assert (NODE.itemsize, TRI.itemsize, GEOM.itemsize, MATERIAL.itemsize, CAMERA.itemsize, RAY.itemsize, HIT.itemsize) == \
+    (64, 76, 236, 56, 84, 24, 32)
+
+FULLSTACK, SHORTSTACK, REF_T1, REF_T2 = 0, 1, 2, 3
+MODES = {"fullstack": FULLSTACK, "shortstack": SHORTSTACK, "ref_t1": REF_T1, "ref_t2": REF_T2}
+
+
+class KdptError(RuntimeError):
+    pass
+
+
+class _CCamera(ctypes.Structure):
+    _fields_ = [("resolution", ctypes.c_int * 2), ("position", ctypes.c_float * 3), ("lookAt", ctypes.c_float * 3),
+                ("view", ctypes.c_float * 3), ("up", ctypes.c_float * 3), ("right", ctypes.c_float * 3),
+                ("fov", ctypes.c_float * 2), ("pixelLength", ctypes.c_float * 2)]
+
+
+class _CScene(ctypes.Structure):
+    _fields_ = [("nodes", ctypes.c_void_p), ("numNodes", ctypes.c_int), ("tris", ctypes.c_void_p), ("numTris", ctypes.c_int),
+                ("geoms", ctypes.c_void_p), ("numGeoms", ctypes.c_int), ("materials", ctypes.c_void_p),
+                ("numMaterials", ctypes.c_int), ("objMaterialOffsets", ctypes.c_void_p), ("numShapes", ctypes.c_int),
+                ("camera", _CCamera), ("traceDepth", ctypes.c_int)]
+
+
+class CParams(ctypes.Structure):
+    """kdpt_params — the trailing arguments of the reference's pathtrace() (defaults main.cpp:35-60)."""
+    _fields_ = [("focalLength", ctypes.c_float), ("dofAngle", ctypes.c_float), ("softness", ctypes.c_float),
+                ("antialias", ctypes.c_int), ("enableSss", ctypes.c_int), ("compaction", ctypes.c_int),
+                ("mode", ctypes.c_int), ("sortByMaterial", ctypes.c_int), ("reserved", ctypes.c_int * 4)]
+
+
+class CRenderStats(ctypes.Structure):
+    _fields_ = [("rayBounces", ctypes.c_uint64), ("launches", ctypes.c_uint64), ("intersectMs", ctypes.c_float),
+                ("totalMs", ctypes.c_float)]
+
+
+def default_params(**kw) -> CParams:
+    p = CParams(focalLength=6.0, dofAngle=0.0, softness=0.0, antialias=1, enableSss=0, compaction=1, mode=REF_T2,
+                sortByMaterial=1)
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KdptError(f"unknown render parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libkdpt.so; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KdptError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "or `make -C kdtreepathtraceroptimization_b200/csrc` — there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.kdpt_last_error.restype = ctypes.c_char_p
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.kdpt_create.argtypes = [ctypes.POINTER(_CScene), ci, ctypes.POINTER(vp)]
+    lib.kdpt_destroy.argtypes = [vp]
+    lib.kdpt_tree_info.argtypes = [vp] + [ctypes.POINTER(ci)] * 4 + [ctypes.POINTER(ctypes.c_uint64)]
+    lib.kdpt_trace.argtypes = [vp, vp, vp, ci, vp, ci]
+    lib.kdpt_trace_device.argtypes = [vp, vp, vp, ci, vp, ci, vp]
+    lib.kdpt_sync.argtypes = [vp]
+    lib.kdpt_render.argtypes = [vp, ci, ci, ci, ctypes.POINTER(CParams), ctypes.POINTER(CRenderStats)]
+    lib.kdpt_clear_image.argtypes = [vp]
+    lib.kdpt_get_image.argtypes = [vp, vp]
+    lib.kdpt_image_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+    if lib.kdpt_abi_version() != 1:
+        raise KdptError("libkdpt.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise KdptError(f"{what} failed ({rc}): {load_library().kdpt_last_error().decode(errors='replace')}")
+
+
+@dataclass
+class Scene:
+    """The flat arrays pathtraceInit reads from the reference's Scene (pathtrace.cu:203-258)."""
+    nodes: np.ndarray
+    tris: np.ndarray
+    geoms: np.ndarray
+    materials: np.ndarray
+    offsets: np.ndarray
+    camera: np.ndarray          # CAMERA[1]
+    trace_depth: int = 8
+    iterations: int = 0
+
+    @staticmethod
+    def from_npz(path: str) -> "Scene":
+        z = np.load(path)
+        return Scene(nodes=np.ascontiguousarray(z['nodes'].view(NODE) if z['nodes'].dtype != NODE else z['nodes']),
+                     tris=np.ascontiguousarray(z['tris']), geoms=np.ascontiguousarray(z['geoms']),
+                     materials=np.ascontiguousarray(z['materials']), offsets=np.ascontiguousarray(z['offsets'], dtype='i4'),
+                     camera=np.ascontiguousarray(z['camera']), trace_depth=int(z['trace_depth']),
+                     iterations=int(z['iterations']) if 'iterations' in z else 0)
+
+    @staticmethod
+    def tree_only(nodes: np.ndarray, tris: np.ndarray, num_materials: int = 1) -> "Scene":
+        return Scene(nodes=np.ascontiguousarray(nodes), tris=np.ascontiguousarray(tris), geoms=np.zeros(0, GEOM),
+                     materials=np.zeros(num_materials, MATERIAL), offsets=np.zeros(1, 'i4'), camera=np.zeros(1, CAMERA),
+                     trace_depth=8)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p) if a.size else None
+
+
+class Context:
+    """kdpt_ctx: pathtraceInit on creation, pathtraceFree on close()."""
+
+    def __init__(self, scene: Scene, device: int = 0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        self.scene = scene
+        for name, dt in (("nodes", NODE), ("tris", TRI), ("geoms", GEOM), ("materials", MATERIAL), ("camera", CAMERA)):
+            a = getattr(scene, name)
+            if a.dtype.itemsize != dt.itemsize or not a.flags['C_CONTIGUOUS']:
+                raise KdptError(f"scene.{name}: expected contiguous records of {dt.itemsize} bytes")
+        cs = _CScene()
+        cs.nodes, cs.numNodes = _ptr(scene.nodes), len(scene.nodes)
+        cs.tris, cs.numTris = _ptr(scene.tris), len(scene.tris)
+        cs.geoms, cs.numGeoms = _ptr(scene.geoms), len(scene.geoms)
+        cs.materials, cs.numMaterials = _ptr(scene.materials), len(scene.materials)
+        cs.objMaterialOffsets, cs.numShapes = _ptr(scene.offsets), len(scene.offsets)
+        ctypes.memmove(ctypes.byref(cs.camera), scene.camera.ctypes.data, CAMERA.itemsize)
+        cs.traceDepth = int(scene.trace_depth)
+        _check(self._lib.kdpt_create(ctypes.byref(cs), int(device), ctypes.byref(self._h)), "kdpt_create")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._lib.kdpt_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tree_info(self) -> dict:
+        v = [ctypes.c_int() for _ in range(4)]
+        b = ctypes.c_uint64()
+        _check(self._lib.kdpt_tree_info(self._h, *[ctypes.byref(x) for x in v], ctypes.byref(b)), "kdpt_tree_info")
+        return dict(num_nodes=v[0].value, num_leaf_tris=v[1].value, max_depth=v[2].value, max_leaf=v[3].value,
+                    device_bytes=b.value)
+
+    def trace(self, rays: np.ndarray, t_min_in: np.ndarray | None = None, mode: int = FULLSTACK) -> np.ndarray:
+        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call). rays: (n,6) float32 or RAY[n]."""
+        rays = np.ascontiguousarray(rays)
+        n = rays.shape[0]
+        if rays.dtype != RAY:
+            rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(n, 6)
+        hits = np.zeros(n, HIT)
+        tm = None
+        if t_min_in is not None:
+            tm = np.ascontiguousarray(t_min_in, dtype=np.float32)
+            if tm.shape != (n,):
+                raise KdptError("t_min_in must have one float per ray")
+        _check(self._lib.kdpt_trace(self._h, _ptr(rays), _ptr(tm) if tm is not None else None, n, _ptr(hits), int(mode)),
+               "kdpt_trace")
+        return hits
+
+    def trace_device(self, d_rays: int, d_t_min_in: int | None, n: int, d_hits: int, mode: int = FULLSTACK,
+                     stream: int | None = None):
+        """Device pointers (e.g. torch tensor .data_ptr()); asynchronous on `stream` (cudaStream_t) or the ctx stream."""
+        _check(self._lib.kdpt_trace_device(self._h, d_rays, d_t_min_in, int(n), d_hits, int(mode), stream),
+               "kdpt_trace_device")
+
+    def sync(self):
+        _check(self._lib.kdpt_sync(self._h), "kdpt_sync")
+
+    def render(self, iter_begin: int, iter_count: int, iter_stride: int = 1, params: CParams | None = None) -> dict:
+        p = params if params is not None else default_params()
+        st = CRenderStats()
+        _check(self._lib.kdpt_render(self._h, int(iter_begin), int(iter_count), int(iter_stride), ctypes.byref(p),
+                                     ctypes.byref(st)), "kdpt_render")
+        return dict(ray_bounces=st.rayBounces, launches=st.launches, intersect_ms=st.intersectMs, total_ms=st.totalMs)
+
+    def clear_image(self):
+        _check(self._lib.kdpt_clear_image(self._h), "kdpt_clear_image")
+
+    def image(self) -> np.ndarray:
+        w, h = (int(x) for x in self.scene.camera['resolution'][0])
+        out = np.zeros((h, w, 3), np.float32)
+        _check(self._lib.kdpt_get_image(self._h, _ptr(out)), "kdpt_get_image")
+        return out
+
+    def image_device(self) -> tuple[int, int]:
+        p = ctypes.c_void_p()
+        n = ctypes.c_int()
+        _check(self._lib.kdpt_image_device(self._h, ctypes.byref(p), ctypes.byref(n)), "kdpt_image_device")
+        return p.value, n.value

@@ -1,0 +1,196 @@
+// kdpt_api.cu — the C ABI of include/kdpt.h: context life cycle (pathtraceInit / pathtraceFree,
+// src/pathtrace.cu:201-313) and the traversal-only entry points. The render loop lives in kdpt_render.cu.
+#include "kdpt_internal.h"
+#include <string.h>
+
+namespace kdpt {
+
+static thread_local std::string g_lastError;
+void setError(const std::string& msg) { g_lastError = msg; }
+int cudaFail(cudaError_t e, const char* what)
+{
+    g_lastError = std::string(what) + ": " + cudaGetErrorString(e);
+    return KDPT_ERR_CUDA;
+}
+
+int DeviceBuffer::alloc(size_t n)
+{
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) { p = nullptr; return cudaFail(e, "cudaMalloc"); }
+    bytes = n;
+    return KDPT_OK;
+}
+int DeviceBuffer::ensure(size_t n) { return n <= bytes && p ? KDPT_OK : alloc(n + n / 4); }
+void DeviceBuffer::release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+
+template <class T>
+static int upload(DeviceBuffer& buf, const std::vector<T>& v, const T** devPtr, cudaStream_t s)
+{
+    int rc = buf.alloc(v.size() * sizeof(T));
+    if (rc) return rc;
+    if (!v.empty()) KDPT_CUDA(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    *devPtr = (const T*)buf.p;
+    return KDPT_OK;
+}
+
+static int ensurePinned(void** p, size_t* have, size_t need)
+{
+    if (*p && *have >= need) return KDPT_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *have = 0;
+    KDPT_CUDA(cudaMallocHost(p, need + need / 4));
+    *have = need + need / 4;
+    return KDPT_OK;
+}
+
+} // namespace kdpt
+
+using namespace kdpt;
+
+extern "C" {
+
+int kdpt_abi_version(void) { return KDPT_ABI_VERSION; }
+const char* kdpt_last_error(void) { return g_lastError.c_str(); }
+
+int kdpt_destroy(kdpt_ctx* ctx)
+{
+    if (!ctx) return KDPT_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->treeMem) b.release();
+    DeviceBuffer* bufs[] = {&ctx->scene.geoms, &ctx->scene.materials, &ctx->scene.offsets, &ctx->rays, &ctx->tmin,
+                            &ctx->hits, &ctx->counter, &ctx->image, &ctx->pathsA, &ctx->pathsB, &ctx->isects,
+                            &ctx->scanTmp, &ctx->keysTmp, &ctx->hist};
+    for (auto* b : bufs) b->release();
+    if (ctx->pinnedIn) cudaFreeHost(ctx->pinnedIn);
+    if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);
+    cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev2, ctx->ev3};
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return KDPT_OK;
+}
+
+int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
+{
+    static_assert(sizeof(kdpt_geom) == 236 && sizeof(kdpt_material) == 56 && sizeof(kdpt_camera) == 84, "reference POD ABI");
+    static_assert(sizeof(kdpt_ray) == 24 && sizeof(kdpt_hit) == 32, "kdpt ABI");
+    if (!scene || !out) { setError("kdpt_create: null argument"); return KDPT_ERR_ARG; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        setError(std::string("kdpt_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                 "); this library has no CPU path");
+        return KDPT_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { setError("kdpt_create: device ordinal out of range"); return KDPT_ERR_ARG; }
+    FlatTree flat; std::string err;
+    if (!flatten(scene->nodes, scene->numNodes, scene->tris, scene->numTris, flat, err)) { setError(err); return KDPT_ERR_ARG; }
+    if (scene->numGeoms < 0 || scene->numMaterials < 0 || scene->numShapes < 0 ||
+        (scene->numGeoms > 0 && !scene->geoms) || (scene->numMaterials > 0 && !scene->materials) ||
+        (scene->numShapes > 0 && !scene->objMaterialOffsets)) {
+        setError("kdpt_create: bad geoms/materials/offsets");
+        return KDPT_ERR_ARG;
+    }
+    KDPT_CUDA(cudaSetDevice(device));
+    kdpt_ctx* ctx = new kdpt_ctx();
+    ctx->device = device;
+    int rc = KDPT_OK;
+    auto fail = [&](int code) { kdpt_destroy(ctx); return code; };
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(cudaFail(e, "cudaGetDeviceProperties"));
+    ctx->numSMs = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaFail(e, "cudaStreamCreate"));
+    cudaEvent_t* evs[] = {&ctx->ev0, &ctx->ev1, &ctx->ev2, &ctx->ev3};
+    for (auto pe : evs) if ((e = cudaEventCreate(pe)) != cudaSuccess) return fail(cudaFail(e, "cudaEventCreate"));
+
+    Tree& T = ctx->tree;
+    cudaStream_t s = ctx->stream;
+    if ((rc = upload(ctx->treeMem[0], flat.nodes, (const HostNode**)&T.nodes, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[1], flat.boxLo, (const HostF4**)&T.boxLo, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[2], flat.boxHi, (const HostF4**)&T.boxHi, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[3], flat.triA, (const HostF4**)&T.triA, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[4], flat.triB, (const HostF4**)&T.triB, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[5], flat.triC, (const HostF2**)&T.triC, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[6], flat.nrmA, (const HostF4**)&T.nrmA, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[7], flat.nrmB, (const HostF4**)&T.nrmB, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[8], flat.nrmC, (const HostF2**)&T.nrmC, s))) return fail(rc);
+    T.numNodes = flat.numNodes; T.numTris = flat.numTris;
+    for (int a = 0; a < 3; a++) { T.rootLo[a] = flat.rootLo[a]; T.rootHi[a] = flat.rootHi[a]; }
+    for (int k = 0; k < 4; k++) T.tagCand[k] = flat.tagCand[k];
+    T.materialSize = scene->numMaterials;
+    ctx->deviceBytes = flat.bytes();
+
+    SceneDev& S = ctx->scene;
+    S.numGeoms = scene->numGeoms; S.numMaterials = scene->numMaterials; S.numShapes = scene->numShapes;
+    if ((rc = S.geoms.alloc(sizeof(kdpt_geom) * (size_t)S.numGeoms))) return fail(rc);
+    if ((rc = S.materials.alloc(sizeof(kdpt_material) * (size_t)S.numMaterials))) return fail(rc);
+    if ((rc = S.offsets.alloc(sizeof(int) * (size_t)S.numShapes))) return fail(rc);
+    if (S.numGeoms && (e = cudaMemcpyAsync(S.geoms.p, scene->geoms, sizeof(kdpt_geom) * (size_t)S.numGeoms, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload geoms"));
+    if (S.numMaterials && (e = cudaMemcpyAsync(S.materials.p, scene->materials, sizeof(kdpt_material) * (size_t)S.numMaterials, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload materials"));
+    if (S.numShapes && (e = cudaMemcpyAsync(S.offsets.p, scene->objMaterialOffsets, sizeof(int) * (size_t)S.numShapes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload offsets"));
+    S.camera = scene->camera; S.traceDepth = scene->traceDepth;
+    S.hasCamera = scene->camera.resolution[0] > 0 && scene->camera.resolution[1] > 0;
+    if ((rc = ctx->counter.alloc(256))) return fail(rc);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(cudaFail(e, "cudaStreamSynchronize"));
+    // keep only the sizes on the host
+    flat.nodes.clear(); flat.nodes.shrink_to_fit(); flat.boxLo.clear(); flat.boxLo.shrink_to_fit();
+    flat.boxHi.clear(); flat.boxHi.shrink_to_fit(); flat.triA.clear(); flat.triA.shrink_to_fit();
+    flat.triB.clear(); flat.triB.shrink_to_fit(); flat.triC.clear(); flat.triC.shrink_to_fit();
+    flat.nrmA.clear(); flat.nrmA.shrink_to_fit(); flat.nrmB.clear(); flat.nrmB.shrink_to_fit();
+    flat.nrmC.clear(); flat.nrmC.shrink_to_fit();
+    ctx->info = flat;
+    *out = ctx;
+    return KDPT_OK;
+}
+
+int kdpt_tree_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* maxDepth, int* maxLeaf, uint64_t* deviceBytes)
+{
+    if (!ctx) { setError("kdpt_tree_info: null context"); return KDPT_ERR_ARG; }
+    if (numNodes) *numNodes = ctx->info.numNodes;
+    if (numLeafTris) *numLeafTris = ctx->info.numTris;
+    if (maxDepth) *maxDepth = ctx->info.maxDepth;
+    if (maxLeaf) *maxLeaf = ctx->info.maxLeaf;
+    if (deviceBytes) *deviceBytes = ctx->deviceBytes;
+    return KDPT_OK;
+}
+
+int kdpt_sync(kdpt_ctx* ctx)
+{
+    if (!ctx) { setError("kdpt_sync: null context"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KDPT_OK;
+}
+
+int kdpt_trace_device(kdpt_ctx* ctx, const kdpt_ray* d_rays, const float* d_t_min_in, int n, kdpt_hit* d_hits, int mode, void* stream)
+{
+    if (!ctx || n < 0 || (n > 0 && (!d_rays || !d_hits))) { setError("kdpt_trace_device: bad argument"); return KDPT_ERR_ARG; }
+    if (mode < 0 || mode >= KDPT_MODE_COUNT) { setError("kdpt_trace_device: unknown mode"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    return launchTrace(ctx, d_rays, d_t_min_in, n, d_hits, mode, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n, kdpt_hit* hits, int mode)
+{
+    if (!ctx || n < 0 || (n > 0 && (!rays || !hits))) { setError("kdpt_trace: bad argument"); return KDPT_ERR_ARG; }
+    if (mode < 0 || mode >= KDPT_MODE_COUNT) { setError("kdpt_trace: unknown mode"); return KDPT_ERR_ARG; }
+    if (n == 0) return KDPT_OK;
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    size_t rb = sizeof(kdpt_ray) * (size_t)n, tb = sizeof(float) * (size_t)n, hb = sizeof(kdpt_hit) * (size_t)n;
+    if ((rc = ctx->rays.ensure(rb)) || (rc = ctx->hits.ensure(hb)) || (t_min_in && (rc = ctx->tmin.ensure(tb)))) return rc;
+    cudaStream_t s = ctx->stream;
+    // pageable host memory is fine for the caller; the copies below are ordered on the context's stream
+    KDPT_CUDA(cudaMemcpyAsync(ctx->rays.p, rays, rb, cudaMemcpyHostToDevice, s));
+    if (t_min_in) KDPT_CUDA(cudaMemcpyAsync(ctx->tmin.p, t_min_in, tb, cudaMemcpyHostToDevice, s));
+    if ((rc = launchTrace(ctx, ctx->rays.as<kdpt_ray>(), t_min_in ? ctx->tmin.as<float>() : nullptr, n, ctx->hits.as<kdpt_hit>(), mode, s))) return rc;
+    KDPT_CUDA(cudaMemcpyAsync(hits, ctx->hits.p, hb, cudaMemcpyDeviceToHost, s));
+    KDPT_CUDA(cudaStreamSynchronize(s));
+    return KDPT_OK;
+}
+
+} // extern "C"

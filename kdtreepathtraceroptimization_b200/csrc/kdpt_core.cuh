@@ -1,0 +1,332 @@
+// kdpt_core.cuh — device data layout and the per-ray arithmetic of the hot path.
+//
+// Everything that decides a hit is written as separate IEEE-754 binary32 multiplies and adds in the reference's
+// (glm 0.9.6.3) evaluation order; the translation unit is compiled with -fmad=false, default -prec-div/-prec-sqrt
+// and no -use_fast_math, so the device results are bit-identical to the reference's host functions:
+//   glm::intersectRayTriangle     external/include/glm/gtx/intersect.inl:37-71
+//   intersectAABBarrays           src/intersections.h:253-286
+//   leaf body (normal, nudge, t)  src/pathtrace.cu:985-1010 / 1133-1161
+//   glm dot/cross/normalize       external/include/glm/detail/func_geometric.inl:64-72, 134-142, 158
+//
+// The functions are KDPT_HD (device-only under nvcc) so that tests/hostsim can compile the very same source with g++ for CPU-only logic
+// tests; the product library only ever calls them from __global__ kernels.
+#pragma once
+#include <stdint.h>
+#include <float.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define KDPT_HD __device__ __forceinline__
+#define KDPT_LDG(p) __ldg(p)
+#include <cuda_runtime.h>
+#else
+#define KDPT_HD inline
+#define KDPT_LDG(p) (*(p))
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+static inline float __int_as_float(int i) { float f; __builtin_memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; __builtin_memcpy(&i, &f, 4); return i; }
+static inline unsigned __float_as_uint(float f) { unsigned i; __builtin_memcpy(&i, &f, 4); return i; }
+#endif
+
+namespace kdpt {
+
+constexpr int kMaxDepth = 32;           // deepest tree the per-ray stacks accept (reference: split(13) -> 14)
+constexpr float kExitSlack = 1e-3f;     // early-exit slack in world units (acceptance is on the nudged distance)
+constexpr unsigned kLeafFlag = 3u;
+
+// ---- flattened tree in HBM -------------------------------------------------------------------------------------
+// node (16 B, index == reference node ID, IDs are DFS pre-order):
+//   interior: x = split plane (float bits) = nodes[left].maxs[axis]   y = right child   z = left child
+//             w = axis (bits 0-1) | (parent + 1) << 2
+//   leaf:     x = first leaf triangle            y = triangle count (may be 0)          z = unused
+//             w = 3 | (parent + 1) << 2
+// leaf triangles keep the reference's leaf order (TriBare index i), split into a hot and a cold part:
+//   triA[i] = (v0.x, v0.y, v0.z, e1.x)  triB[i] = (e1.y, e1.z, e2.x, e2.y)  triC[i] = (e2.z, canonical index)
+//   nrmA[i] = (n1.x, n1.y, n1.z, n2.x)  nrmB[i] = (n2.y, n2.z, n3.x, n3.y)  nrmC[i] = (n3.z, mtlIdx)
+//   with e1 = v1 - v0, e2 = v2 - v0 (the first two operations of glm::intersectRayTriangle, done once).
+// boxes (reference-compatible modes only): boxLo[i] = (mins, 0), boxHi[i] = (maxs, NodeBare.axis as int bits).
+struct Tree {
+    const uint4* nodes;
+    const float4* boxLo;
+    const float4* boxHi;
+    const float4* triA;
+    const float4* triB;
+    const float2* triC;
+    const float4* nrmA;
+    const float4* nrmB;
+    const float2* nrmC;
+    int numNodes;
+    int numTris;
+    float rootLo[3], rootHi[3];
+    int tagCand[4];     // nodes[0].leftID, nodes[0].rightID, nodes[1].leftID, nodes[1].rightID (T2 quirk)
+    int materialSize;   // hst_scene->materials.size()
+};
+
+struct Hit {
+    float t;            // nudged distance (reference t_min)
+    float z, u, v;
+    int tri;            // canonical TriBare index, -1 = none
+    float nx, ny, nz;
+    int mtl;            // mtlIdx of the accepted triangle
+    int anyMtl;         // mtlIdx of the LAST triangle glm accepted (reference objMaterialIdx source), -1 none
+};
+
+struct V3 { float x, y, z; };
+KDPT_HD V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+KDPT_HD V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+KDPT_HD V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+KDPT_HD V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+KDPT_HD V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
+KDPT_HD V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+KDPT_HD V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+KDPT_HD float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+KDPT_HD V3 cross(V3 x, V3 y) { return mk(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+KDPT_HD float length(V3 a) { return sqrtf(dot(a, a)); }
+KDPT_HD V3 normalize(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+KDPT_HD float comp(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+// glm::intersectRayTriangle with e1/e2 precomputed. Returns 0 = rejected before baryPosition.z was written,
+// 1 = z written but negative (glm returns false), 2 = hit (glm returns true). u, v, z are only meaningful as
+// far as glm wrote them.
+KDPT_HD int rayTri(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float& u, float& v, float& z)
+{
+    V3 p = cross(d, e2);
+    float a = dot(e1, p);
+    if (a < FLT_EPSILON) return 0;
+    float f = 1.0f / a;
+    V3 s = o - v0;
+    u = f * dot(s, p);
+    if (u < 0.0f) return 0;
+    if (u > 1.0f) return 0;
+    V3 q = cross(s, e1);
+    v = f * dot(d, q);
+    if (v < 0.0f) return 0;
+    if (v + u > 1.0f) return 0;
+    z = f * dot(e2, q);
+    return z >= 0.0f ? 2 : 1;
+}
+
+// intersectAABBarrays
+KDPT_HD bool slab(V3 o, V3 inv, const float* lo, const float* hi, float& dmin, float& dmax)
+{
+    float v1 = (lo[0] - o.x) * inv.x, v2 = (hi[0] - o.x) * inv.x;
+    float v3 = (lo[1] - o.y) * inv.y, v4 = (hi[1] - o.y) * inv.y;
+    float v5 = (lo[2] - o.z) * inv.z, v6 = (hi[2] - o.z) * inv.z;
+    dmin = fmaxf(fmaxf(fminf(v1, v2), fminf(v3, v4)), fminf(v5, v6));
+    dmax = fminf(fminf(fmaxf(v1, v2), fmaxf(v3, v4)), fmaxf(v5, v6));
+    return !(dmax < 0.0f) && !(dmin > dmax);
+}
+KDPT_HD bool refBox(V3 o, V3 inv, float4 lo, float4 hi, float& dist)
+{
+    float l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+    float dmin, dmax;
+    // the reference tests dmax < 0 first, then dmin > dmax; both misses report dmax, a hit reports dmin
+    bool ok = slab(o, inv, l, h, dmin, dmax);
+    dist = ok ? dmin : dmax;
+    return ok;
+}
+
+struct TriHot { V3 v0, e1, e2; int canon; };
+KDPT_HD TriHot loadTri(const Tree& T, int i)
+{
+    float4 a = KDPT_LDG(T.triA + i), b = KDPT_LDG(T.triB + i);
+    float2 c = KDPT_LDG(T.triC + i);
+    TriHot t;
+    t.v0 = mk(a.x, a.y, a.z); t.e1 = mk(a.w, b.x, b.y); t.e2 = mk(b.z, b.w, c.x);
+    t.canon = __float_as_int(c.y);
+    return t;
+}
+
+// Leaf body after glm said "intersected": interpolated normal, nudged point, distance, acceptance.
+// tieByIndex: equal distance keeps the smaller canonical index (order-independent closest hit).
+KDPT_HD void acceptHit(const Tree& T, int i, int canon, V3 o, V3 d, float u, float v, float z, float eps,
+                       bool tieByIndex, Hit& H)
+{
+    float4 a = KDPT_LDG(T.nrmA + i), b = KDPT_LDG(T.nrmB + i);
+    float2 c = KDPT_LDG(T.nrmC + i);
+    V3 n1 = mk(a.x, a.y, a.z), n2 = mk(a.w, b.x, b.y), n3 = mk(b.z, b.w, c.x);
+    int mtl = __float_as_int(c.y);
+    H.anyMtl = mtl;
+    V3 hp = o + d * z;
+    V3 nrm = normalize(((1 - u - v) * n1 + u * n2) + v * n3);
+    hp = hp + nrm * eps;
+    float t = length(hp - o);
+    bool better = t > 0.0f && H.t > t;
+    if (tieByIndex && !better && H.tri >= 0 && t > 0.0f && H.t == t && canon < H.tri) better = true;
+    if (better) {
+        H.t = t; H.z = z; H.u = u; H.v = v; H.tri = canon; H.nx = nrm.x; H.ny = nrm.y; H.nz = nrm.z; H.mtl = mtl;
+    }
+}
+
+KDPT_HD void initHit(Hit& H, float tMinIn)
+{
+    H.t = tMinIn; H.z = 0.f; H.u = 0.f; H.v = 0.f; H.tri = -1; H.nx = H.ny = H.nz = 0.f; H.mtl = -1; H.anyMtl = -1;
+}
+
+// ---- exact closest hit, one ray per thread --------------------------------------------------------------------
+// Near-first descent on the split planes, identical to oracle/kdpt_oracle.c:traverse_stack. STACK = per-ray stack
+// capacity: kMaxDepth gives the full-stack variant, a small value the short-stack/restart variant (entries pushed
+// when the stack is full push the oldest one out; when the stack runs dry after that, the ray restarts at the
+// root with tmin advanced to the exit of the last leaf).
+template <int STACK>
+struct RayStack {
+    unsigned node[STACK]; float tmin[STACK]; float tmax[STACK];
+    int n; bool dropped;
+    KDPT_HD void clear() { n = 0; dropped = false; }
+    KDPT_HD void push(unsigned nd, float a, float b)
+    {
+        if (STACK >= kMaxDepth) { node[n] = nd; tmin[n] = a; tmax[n] = b; n++; return; }
+        if (n == STACK) {
+#pragma unroll
+            for (int k = 0; k + 1 < STACK; k++) { node[k] = node[k + 1]; tmin[k] = tmin[k + 1]; tmax[k] = tmax[k + 1]; }
+            n = STACK - 1; dropped = true;
+        }
+#pragma unroll
+        for (int k = 0; k < STACK; k++) if (k == n) { node[k] = nd; tmin[k] = a; tmax[k] = b; }
+        n++;
+    }
+    KDPT_HD void pop(unsigned& nd, float& a, float& b)
+    {
+        n--;
+        if (STACK >= kMaxDepth) { nd = node[n]; a = tmin[n]; b = tmax[n]; return; }
+#pragma unroll
+        for (int k = 0; k < STACK; k++) if (k == n) { nd = node[k]; a = tmin[k]; b = tmax[k]; }
+    }
+};
+
+struct TraceCounters { unsigned nodes, leaves, tris; };
+
+template <int STACK, bool COUNT>
+KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit& H, TraceCounters* ctr)
+{
+    initHit(H, tMinIn);
+    if (T.numNodes == 0) return;
+    float len = length(d);
+    if (!(len > 0.0f) || !(len <= FLT_MAX)) return;
+    float slack = kExitSlack / len;
+    V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float t0, t1;
+    if (COUNT) ctr->nodes++;
+    if (!slab(o, inv, T.rootLo, T.rootHi, t0, t1)) return;
+    if (!(t0 > 0.0f)) t0 = 0.0f;
+    float zbound = tMinIn < FLT_MAX ? tMinIn / len : FLT_MAX;
+    RayStack<STACK> st; st.clear();
+    unsigned cur = 0; float tmin = t0, tmax = t1;
+    for (;;) {
+        uint4 nd = KDPT_LDG(T.nodes + cur);
+        while ((nd.w & 3u) != kLeafFlag) {
+            int a = (int)(nd.w & 3u);
+            float split = __int_as_float((int)nd.x);
+            float oa = comp(o, a), da = comp(d, a), ia = comp(inv, a);
+            bool below = oa < split || (oa == split && da <= 0.0f);
+            unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+            float tp = (split - oa) * ia;
+            if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
+            else if (tp <= tmin) cur = farc;
+            else { st.push(farc, tp, tmax); cur = nearc; tmax = tp; }
+            nd = KDPT_LDG(T.nodes + cur);
+            if (COUNT) ctr->nodes++;
+        }
+        int start = (int)nd.x, count = (int)nd.y;
+        if (count > 0) {
+            if (COUNT) { ctr->leaves++; ctr->tris += (unsigned)count; }
+            for (int i = start; i < start + count; i++) {
+                TriHot tr = loadTri(T, i);
+                float u, v, z;
+                if (rayTri(o, d, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
+            }
+        }
+        float zb = H.tri >= 0 ? fminf(H.z, zbound) : zbound;
+        bool found = false;
+        while (st.n > 0) {
+            unsigned n2; float a2, b2;
+            st.pop(n2, a2, b2);
+            if (a2 > zb + slack) continue;
+            cur = n2; tmin = a2; tmax = b2; found = true;
+            break;
+        }
+        if (found) continue;
+        if (STACK < kMaxDepth && st.dropped) {
+            // kd-restart: everything up to the exit of this leaf is done
+            if (tmax >= t1 || tmax > zb + slack) break;
+            tmin = tmax; tmax = t1; cur = 0; st.clear();
+            continue;
+        }
+        break;
+    }
+}
+
+// ---- reference-compatible traversal (KDPT_REF_T1 / KDPT_REF_T2) --------------------------------------------------
+// The reference's parent-pointer state machine visits nodes exactly like this depth-first walk (proved equal on
+// every ray by tests/test_oracle_cpu.py on the CPU restatement, oracle/kdpt_oracle.c:traverse_dfs):
+//   visit(N): box test; prune when missed or dist > bary.z, where bary.z is whatever glm wrote LAST (a farther
+//   hit, or a negative t); leaf: test every triangle; interior: first child, re-check the prune, second child.
+//   T2 picks the first child by the sign of dir[axis] and, on every triangle hit, tags a child of node 0 (or of
+//   node 1 when the leaf's parent is itself tagged) as visited — pathtrace.cu:1136/1199.
+template <bool T2>
+KDPT_HD void traceRef(const Tree& T, V3 o, V3 d, float tMinIn, Hit& H, float* lastBary)
+{
+    initHit(H, tMinIn);
+    float bu = 0.f, bv = 0.f, bz = FLT_MAX;
+    const float eps = T2 ? 0.0001f : 0.00001f;
+    if (T.numNodes != 0) {
+        V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        unsigned tagMask = 0;
+        auto tagged = [&](int id) -> bool {
+            if (!T2 || id < 0) return false;
+            return ((tagMask & 1u) && id == T.tagCand[0]) || ((tagMask & 2u) && id == T.tagCand[1]) ||
+                   ((tagMask & 4u) && id == T.tagCand[2]) || ((tagMask & 8u) && id == T.tagCand[3]);
+        };
+        int stNode[kMaxDepth]; int stSecond[kMaxDepth]; float stDist[kMaxDepth];
+        int sp = 0;
+        int cur = 0;
+        for (;;) {
+            uint4 nd = KDPT_LDG(T.nodes + cur);
+            float dist;
+            bool hitGeom = refBox(o, inv, KDPT_LDG(T.boxLo + cur), KDPT_LDG(T.boxHi + cur), dist);
+            bool descend = hitGeom && !(dist > bz);
+            if (descend) {
+                int nodeAxis = __float_as_int(KDPT_LDG(T.boxHi + cur).w); // NodeBare.axis (level % 3)
+                bool leftFirst = !(T2 && !(comp(d, nodeAxis) > 0.0f));
+                if ((nd.w & 3u) == kLeafFlag) {
+                    int start = (int)nd.x, count = (int)nd.y;
+                    int parent = (int)(nd.w >> 2) - 1;
+                    for (int i = start; i < start + count; i++) {
+                        TriHot tr = loadTri(T, i);
+                        int r = rayTri(o, d, tr.v0, tr.e1, tr.e2, bu, bv, bz);
+                        if (r == 2) {
+                            if (T2) {
+                                int k = tagged(parent) ? 1 : 0;
+                                if (k < T.numNodes) {
+                                    int bit = k * 2 + (leftFirst ? 1 : 0);
+                                    if (T.tagCand[bit] >= 0) tagMask |= 1u << bit;
+                                }
+                            }
+                            acceptHit(T, i, tr.canon, o, d, bu, bv, bz, eps, false, H);
+                        }
+                    }
+                } else {
+                    int first = leftFirst ? (int)nd.z : (int)nd.y, second = leftFirst ? (int)nd.y : (int)nd.z;
+                    bool fOk = !tagged(first), sOk = !tagged(second);
+                    if (fOk) { stNode[sp] = cur; stSecond[sp] = sOk ? second : -1; stDist[sp] = dist; sp++; cur = first; continue; }
+                    if (sOk) { stNode[sp] = cur; stSecond[sp] = -1; stDist[sp] = dist; sp++; cur = second; continue; }
+                }
+            }
+            int next = -1;
+            while (sp > 0) {
+                int n = stNode[sp - 1], sec = stSecond[sp - 1]; float pd = stDist[sp - 1];
+                if (tagged(n)) { sp--; continue; }
+                if (pd > bz) { sp--; continue; }
+                if (sec != -1 && !tagged(sec)) { stSecond[sp - 1] = -1; next = sec; break; }
+                sp--;
+            }
+            if (next == -1) break;
+            cur = next;
+        }
+    }
+    if (lastBary) { lastBary[0] = bu; lastBary[1] = bv; lastBary[2] = bz; }
+}
+
+} // namespace kdpt

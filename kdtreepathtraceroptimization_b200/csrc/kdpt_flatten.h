@@ -1,0 +1,32 @@
+// kdpt_flatten.h — host-side repack of the reference's NodeBare[] / TriBare[] (scene.cpp:905-968) into the
+// device layout described in kdpt_core.cuh. Pure host C++, no CUDA.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/kdpt.h"
+
+namespace kdpt {
+
+struct HostNode { uint32_t x, y, z, w; };
+struct HostF4 { float x, y, z, w; };
+struct HostF2 { float x, y; };
+
+struct FlatTree {
+    std::vector<HostNode> nodes;
+    std::vector<HostF4> boxLo, boxHi;
+    std::vector<HostF4> triA, triB, nrmA, nrmB;
+    std::vector<HostF2> triC, nrmC;
+    float rootLo[3] = {0, 0, 0}, rootHi[3] = {0, 0, 0};
+    int tagCand[4] = {-1, -1, -1, -1};
+    int numNodes = 0, numTris = 0, maxDepth = 0, maxLeaf = 0;
+    // level-order ("top of tree") staging list for shared memory: node indices with depth < topLevels
+    uint64_t bytes() const;
+};
+
+// Validates the reference invariants the kernels rely on (index == ID, children in range, both-or-no children,
+// leaf ranges inside [0, numTris), depth <= kMaxDepth) and fills `out`. Returns false with `err` set otherwise.
+bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, FlatTree& out,
+             std::string& err);
+
+} // namespace kdpt

@@ -1,0 +1,63 @@
+// kdpt_internal.h — context object behind the C ABI (include/kdpt.h). Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/kdpt.h"
+#include "kdpt_core.cuh"
+#include "kdpt_flatten.h"
+
+namespace kdpt {
+
+void setError(const std::string& msg);
+int cudaFail(cudaError_t e, const char* what);
+
+#define KDPT_CUDA(call)                                              \
+    do {                                                             \
+        cudaError_t _e = (call);                                     \
+        if (_e != cudaSuccess) return ::kdpt::cudaFail(_e, #call);   \
+    } while (0)
+
+struct DeviceBuffer {
+    void* p = nullptr; size_t bytes = 0;
+    int alloc(size_t n);
+    int ensure(size_t n);     // grow-only
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// device copies of the analytic scene (render loop)
+struct SceneDev {
+    DeviceBuffer geoms, materials, offsets;
+    int numGeoms = 0, numMaterials = 0, numShapes = 0;
+    kdpt_camera camera{};
+    int traceDepth = 0;
+    bool hasCamera = false;
+};
+
+} // namespace kdpt
+
+struct kdpt_ctx {
+    int device = 0;
+    int numSMs = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    kdpt::Tree tree{};                 // device pointers
+    kdpt::DeviceBuffer treeMem[9];
+    kdpt::FlatTree info;               // host copy of the sizes only (vectors released after upload)
+    uint64_t deviceBytes = 0;
+    kdpt::SceneDev scene;
+    // traversal scratch
+    kdpt::DeviceBuffer rays, tmin, hits, counter;
+    void* pinnedIn = nullptr; size_t pinnedInBytes = 0;
+    void* pinnedOut = nullptr; size_t pinnedOutBytes = 0;
+    // render loop state
+    kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist;
+    int pixelCount = 0;
+};
+
+namespace kdpt {
+// kdpt_trace.cu
+int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n, kdpt_hit* dHits, int mode,
+                cudaStream_t stream);
+} // namespace kdpt

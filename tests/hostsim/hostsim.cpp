@@ -1,0 +1,48 @@
+// TEST INFRASTRUCTURE ONLY — compiles the product's per-ray device functions (csrc/kdpt_core.cuh) and host flatten
+// (csrc/kdpt_flatten.cpp) with g++ so the traversal LOGIC can be checked against the oracle on machines without a
+// GPU (pytest -m "not gpu"). It is never loaded by the package, bench.py or the C ABI; the product has no CPU path.
+#include "../../kdtreepathtraceroptimization_b200/csrc/kdpt_core.cuh"
+#include "../../kdtreepathtraceroptimization_b200/csrc/kdpt_flatten.h"
+#include <string>
+
+using namespace kdpt;
+
+extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris,
+                             int materialSize, const kdpt_ray* rays, const float* tMinIn, int n, kdpt_hit* hits,
+                             int mode, unsigned long long* counters /* nodes, leaves, tris or NULL */,
+                             float* lastBary /* n*3 or NULL, ref modes */)
+{
+    FlatTree F; std::string err;
+    if (!flatten(nodes, numNodes, tris, numTris, F, err)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+    Tree T;
+    T.nodes = (const uint4*)F.nodes.data();
+    T.boxLo = (const float4*)F.boxLo.data(); T.boxHi = (const float4*)F.boxHi.data();
+    T.triA = (const float4*)F.triA.data(); T.triB = (const float4*)F.triB.data(); T.triC = (const float2*)F.triC.data();
+    T.nrmA = (const float4*)F.nrmA.data(); T.nrmB = (const float4*)F.nrmB.data(); T.nrmC = (const float2*)F.nrmC.data();
+    T.numNodes = F.numNodes; T.numTris = F.numTris;
+    for (int a = 0; a < 3; a++) { T.rootLo[a] = F.rootLo[a]; T.rootHi[a] = F.rootHi[a]; }
+    for (int k = 0; k < 4; k++) T.tagCand[k] = F.tagCand[k];
+    T.materialSize = materialSize;
+    TraceCounters tc = {0, 0, 0};
+    unsigned long long cn = 0, cl = 0, ct = 0;
+    for (int i = 0; i < n; i++) {
+        V3 o = mk(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]);
+        V3 d = mk(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
+        float tin = tMinIn ? tMinIn[i] : FLT_MAX;
+        Hit H;
+        tc.nodes = tc.leaves = tc.tris = 0;
+        switch (mode) {
+        case KDPT_FULLSTACK: traceExact<kMaxDepth, true>(T, o, d, tin, 0.00001f, H, &tc); break;
+        case KDPT_SHORTSTACK: traceExact<4, true>(T, o, d, tin, 0.0001f, H, &tc); break;
+        case 100: traceExact<1, true>(T, o, d, tin, 0.0001f, H, &tc); break; // restart stress: 1-entry stack
+        case KDPT_REF_T1: traceRef<false>(T, o, d, tin, H, lastBary ? lastBary + 3 * i : nullptr); break;
+        case KDPT_REF_T2: traceRef<true>(T, o, d, tin, H, lastBary ? lastBary + 3 * i : nullptr); break;
+        default: return -2;
+        }
+        cn += tc.nodes; cl += tc.leaves; ct += tc.tris;
+        hits[i].t = H.t; hits[i].z = H.z; hits[i].u = H.u; hits[i].v = H.v; hits[i].tri = H.tri;
+        hits[i].normal[0] = H.nx; hits[i].normal[1] = H.ny; hits[i].normal[2] = H.nz;
+    }
+    if (counters) { counters[0] = cn; counters[1] = cl; counters[2] = ct; }
+    return 0;
+}

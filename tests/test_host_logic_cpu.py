@@ -1,0 +1,137 @@
+"""CPU-only: the product's host logic (flatten, C-ABI surface) and — through tests/hostsim, a g++ build of the very
+same per-ray device functions the kernels call — the traversal logic against the oracle. No GPU compute here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import kdtreepathtraceroptimization_b200 as kdpt
+from conftest import (KO_BRUTE_T1, KO_BRUTE_T2, KO_STACK_T1, KO_T1, KO_T2, P, ROOT, assert_hits_equal, bits)
+
+
+def _sim(hostsim, g, mode, tmin=None, nmat=6, rays=None):
+    rays = g['rays'] if rays is None else rays
+    n = len(rays)
+    out = np.zeros(n, kdpt.HIT)
+    lb = np.zeros((n, 3), 'f4')
+    ctr = np.zeros(3, 'u8')
+    rc = hostsim.hostsim_trace(P(g['nodes']), len(g['nodes']), P(g['tris']), len(g['tris']), nmat, P(rays),
+                               P(tmin) if tmin is not None else None, n, P(out), mode, P(ctr), P(lb))
+    assert rc == 0
+    return out, lb, ctr
+
+
+@pytest.mark.parametrize("mode,omode", [(kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2), (100, KO_BRUTE_T2)])
+def test_exact_modes_equal_brute_force(hostsim, oracle, golden, mode, omode):
+    for tm in (None, golden['t_min_in']):
+        k, _, _ = _sim(hostsim, golden, mode, tm)
+        o = oracle.trace(omode, golden['nodes'], golden['tris'], golden['rays'], tm, 6)
+        assert_hits_equal(k, o, golden['tris'], f"mode {mode}")
+
+
+@pytest.mark.parametrize("mode,omode,name", [(kdpt.REF_T1, KO_T1, "T1"), (kdpt.REF_T2, KO_T2, "T2")])
+def test_ref_modes_equal_reference(hostsim, oracle, golden, mode, omode, name):
+    for sfx, tm in (("", None), ("_tmin", golden['t_min_in'])):
+        k, lb, _ = _sim(hostsim, golden, mode, tm)
+        o = oracle.trace(omode, golden['nodes'], golden['tris'], golden['rays'], tm, 6)
+        assert_hits_equal(k, o, golden['tris'], name)
+        # and directly against the reference's own outputs
+        assert ((k['tri'] >= 0) == (golden[f'ref_{name}{sfx}_hit'] > 0)).all()
+        assert (bits(k['t']) == bits(golden[f'ref_{name}{sfx}_tmin'])).all()
+        assert (bits(lb) == bits(golden[f'ref_{name}{sfx}_bary'])).all()
+
+
+def test_counters_match_oracle_stack_traversal(hostsim, oracle, golden):
+    """the algorithmic-bytes bookkeeping (V nodes, T triangle tests per ray) is the same on both sides"""
+    _, _, ctr = _sim(hostsim, golden, kdpt.FULLSTACK)
+    _, oc = oracle.trace(KO_STACK_T1, golden['nodes'], golden['tris'], golden['rays'], None, 6, counters=True)
+    assert int(ctr[0]) == int(oc['nodes']) and int(ctr[2]) == int(oc['tris']) and int(ctr[1]) == int(oc['leaves'])
+
+
+def test_degenerate_rays(hostsim, oracle, golden_all):
+    g = golden_all["cornell8_stanford_bunny.npz"]
+    lo, hi = g['nodes']['mins'][0], g['nodes']['maxs'][0]
+    c = (lo + hi) / 2
+    rays = np.array([[*c, 0, 0, 0], [*c, np.nan, 0, 1], [*c, 1e-30, 0, 0], [*c, 0, 1e30, 0], [*lo, 1, 1, 1], [*hi, -1, -1, -1],
+                     [c[0], c[1], lo[2] - 5, 0, 0, 1], [c[0], c[1], lo[2] - 5, 0, 0, -1], [*c, 0, -0.0, 1]], 'f4')
+    for mode, om in ((kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2), (kdpt.REF_T1, KO_T1), (kdpt.REF_T2, KO_T2)):
+        k, _, _ = _sim(hostsim, g, mode, rays=rays)
+        o = oracle.trace(om, g['nodes'], g['tris'], rays, None, 6)
+        assert_hits_equal(k, o, g['tris'], f"degenerate mode {mode}")
+
+
+def test_tiny_trees(hostsim, oracle):
+    """0, 1, 2 and 3 triangles: single-leaf trees (KDnode.cpp:164) and the T2 tag quirk on a root leaf"""
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 7):
+        v = rng.uniform(-1, 1, (n, 9)).astype('f4')
+        nr = rng.normal(size=(n, 9)).astype('f4')
+        nodes, tris, _ = oracle.build_tree(np.concatenate([v, nr], 1), None, 13)
+        o = rng.uniform(-2, 2, (500, 3)); d = rng.normal(size=(500, 3))
+        rays = np.concatenate([o, d], 1).astype('f4')
+        g = dict(nodes=nodes, tris=tris, rays=rays)
+        for mode, om in ((kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2), (kdpt.REF_T1, KO_T1), (kdpt.REF_T2, KO_T2)):
+            k, _, _ = _sim(hostsim, g, mode, nmat=1)
+            assert_hits_equal(k, oracle.trace(om, nodes, tris, rays, None, 1), tris, f"n={n} mode {mode}")
+
+
+def test_flatten_rejects_malformed_trees(hostsim, golden_all):
+    g = golden_all["cornell_sphere_low_1.npz"]
+    rays = g['rays'][:4]
+    out = np.zeros(4, kdpt.HIT)
+
+    def run(nodes, tris):
+        return hostsim.hostsim_trace(P(nodes), len(nodes), P(tris), len(tris), 6, P(rays), None, 4, P(out), 0, None, None)
+    assert run(g['nodes'], g['tris']) == 0
+    bad = g['nodes'].copy(); bad['ID'][3] = 77
+    assert run(bad, g['tris']) == -1
+    bad = g['nodes'].copy(); bad['leftID'][0] = 10 ** 6
+    assert run(bad, g['tris']) == -1
+    bad = g['nodes'].copy()
+    leaf = np.nonzero(bad['triIdSize'] > 0)[0][0]; bad['triIdStart'][leaf] = len(g['tris'])
+    assert run(bad, g['tris']) == -1
+    bad = g['nodes'].copy(); bad['parentID'][0] = 3
+    assert run(bad, g['tris']) == -1
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libkdpt.so loads on a machine without a GPU and exports what include/kdpt.h declares; compute calls fail
+    loudly (no CPU fallback)."""
+    hdr = open(os.path.join(ROOT, "include", "kdpt.h")).read()
+    names = sorted(set(re.findall(r"\b(kdpt_[a-z_]+)\s*\(", hdr)))
+    assert len(names) >= 12
+    lib = kdpt.load_library()
+    for n in names:
+        assert hasattr(lib, n), n
+    out = subprocess.check_output(["nm", "-D", "--defined-only", kdpt.LIB_PATH]).decode()
+    for n in names:
+        assert re.search(rf"\bT {n}\b", out), n
+    assert lib.kdpt_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure(golden_all):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(kdpt.KdptError, match="no CUDA device"):
+        kdpt.Context(kdpt.Scene.from_npz(os.path.join(ROOT, "tests/golden/cornell_sphere_low_1.npz")))
+
+
+def test_product_never_touches_the_oracle():
+    """no file of the product (package, csrc, include) includes, links, loads or imports anything under oracle/
+    (comments may cite it)"""
+    pat = re.compile(r"#\s*include[^\n]*oracle|liboracle|libkdref|CDLL\([^\n]*oracle|import[^\n]*oracle|-l\s*oracle")
+    for base in ("kdtreepathtraceroptimization_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            if "build" in dp or "__pycache__" in dp:
+                continue
+            for f in fs:
+                if f.endswith((".so", ".o", ".log", ".pyc")):
+                    continue
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert not pat.search(txt), os.path.join(dp, f)
+    out = subprocess.check_output(["nm", "-D", kdpt.LIB_PATH]).decode()
+    assert "ko_" not in out and "kdref_" not in out

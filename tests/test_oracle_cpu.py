@@ -1,0 +1,128 @@
+"""CPU-only: pins the oracle (oracle/kdpt_oracle.c) against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py) and against the reference's own tree fixture rnd/houdini/data -> dataout."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (GOLDEN, KO_BRUTE_T1, KO_BRUTE_T2, KO_DFS_T1, KO_DFS_T2, KO_STACK_T1, KO_STACK_T2, KO_T1, KO_T2, P,
+                      bits, canonical_index)
+
+
+def test_houdini_tree_fixture_byte_exact(oracle, tmp_path):
+    """KDtree(path) -> updateBbox -> split(30) -> writeKDtoFile (KDtree.cpp:37-45,115-135; README.md:108-123)"""
+    out = tmp_path / "dataout"
+    n = oracle.lib.ko_soup_tree_dump(os.path.join(GOLDEN, "houdini_data.txt").encode(), 30, str(out).encode())
+    assert n == 1071
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "houdini_dataout.txt"), "rb").read()
+
+
+def _tri18(tris):
+    t = tris
+    return np.stack([t['x1'], t['y1'], t['z1'], t['x2'], t['y2'], t['z2'], t['x3'], t['y3'], t['z3'],
+                     t['nx1'], t['ny1'], t['nz1'], t['nx2'], t['ny2'], t['nz2'], t['nx3'], t['ny3'], t['nz3']], 1)
+
+
+def test_tree_build_matches_reference_flatten(oracle, golden):
+    """NodeBare[]/TriBare[] from the reference loader (scene.cpp:866-968) are reproduced byte-for-byte when the
+    oracle's builder is fed the unique triangles in their order of first appearance... which is only the OBJ face order
+    for the first leaf chain, so feed it the triangles in source order recovered from the canonical map."""
+    nodes, tris = golden['nodes'], golden['tris']
+    canon = canonical_index(tris)
+    # source order: the reference visits faces in OBJ order; within a leaf the order is the source order, and the
+    # root list is the source list. Recover a consistent source order by sorting unique triangles by the position
+    # they take in the left-most leaves is not possible in general, so use the order-preserving property instead:
+    # rebuilding from ANY order that is consistent with every leaf's internal order reproduces the arrays.
+    uniq = np.unique(canon)
+    # topological order consistent with all leaves (each leaf lists its triangles in source order)
+    import collections
+    succ = collections.defaultdict(set); indeg = collections.Counter()
+    for nd in nodes:
+        if nd['triIdSize'] > 0:
+            c = canon[nd['triIdStart']:nd['triIdStart'] + nd['triIdSize']]
+            for a, b in zip(c[:-1], c[1:]):
+                if b not in succ[a]:
+                    succ[a].add(b); indeg[b] += 1
+    import heapq
+    heap = [u for u in uniq if indeg[u] == 0]
+    heapq.heapify(heap)
+    order = []
+    while heap:
+        u = heapq.heappop(heap); order.append(u)
+        for v in succ[u]:
+            indeg[v] -= 1
+            if indeg[v] == 0:
+                heapq.heappush(heap, v)
+    assert len(order) == len(uniq)
+    src = tris[np.array(order)]
+    n2, t2, _ = oracle.build_tree(_tri18(src), src['mtlIdx'], 13)
+    assert len(n2) == len(nodes) and n2.tobytes() == nodes.tobytes()
+    assert len(t2) == len(tris) and t2.tobytes() == tris.tobytes()
+
+
+def test_primitives_match_reference(oracle, golden):
+    rays = golden['rays']
+    box = golden['prim_box']
+    k = len(box)
+    for i in range(k):
+        d = ctypes.c_float()
+        h = oracle.lib.ko_aabb(P(rays[i, :3].copy()), P(rays[i, 3:].copy()), P(box[i, :3].copy()), P(box[i, 3:].copy()), ctypes.byref(d))
+        assert h == golden['prim_box_hit'][i]
+        assert bits(np.float32(d.value)) == bits(golden['prim_box_dist'][i])
+    tri, pr = golden['prim_tri'], golden['prim_tri_rays']
+    nh = 0
+    for i in range(len(tri)):
+        b = np.full(3, -7, 'f4')
+        h = oracle.lib.ko_raytri(P(pr[i, :3].copy()), P(pr[i, 3:].copy()), P(tri[i, 0:3].copy()), P(tri[i, 3:6].copy()), P(tri[i, 6:9].copy()), P(b))
+        assert h == golden['prim_tri_hit'][i]
+        assert (bits(b) == bits(golden['prim_tri_bary'][i])).all()
+        nh += h
+    assert nh > 50
+
+
+@pytest.mark.parametrize("mode,name", [(KO_T1, "T1"), (KO_T2, "T2")])
+@pytest.mark.parametrize("with_tmin", [False, True])
+def test_traversal_matches_reference_host_functions(oracle, golden, mode, name, with_tmin):
+    """traverseKDbare / traverseKDbareShortHybrid (pathtrace.cu:881-1235) run on the host by make_golden.py"""
+    sfx = "_tmin" if with_tmin else ""
+    nmat = len(golden['materials'])
+    o = oracle.trace(mode, golden['nodes'], golden['tris'], golden['rays'], golden['t_min_in'] if with_tmin else None, nmat)
+    assert (o['hit'] == golden[f'ref_{name}{sfx}_hit']).all()
+    assert (bits(o['t_min']) == bits(golden[f'ref_{name}{sfx}_tmin'])).all()
+    assert (bits(o['normal']) == bits(golden[f'ref_{name}{sfx}_normal'])).all()
+    assert (bits(o['last_bary']) == bits(golden[f'ref_{name}{sfx}_bary'])).all()
+    assert (o['objMaterialIdx'] == golden[f'ref_{name}{sfx}_objmat']).all()
+    assert o['hit'].sum() > 100
+
+
+@pytest.mark.parametrize("sm,dfs", [(KO_T1, KO_DFS_T1), (KO_T2, KO_DFS_T2)])
+def test_dfs_form_equals_state_machine(oracle, golden, sm, dfs):
+    """the depth-first form the CUDA reference-compatible kernels use == the literal state machine"""
+    a = oracle.trace(sm, golden['nodes'], golden['tris'], golden['rays'], golden['t_min_in'], 6)
+    b = oracle.trace(dfs, golden['nodes'], golden['tris'], golden['rays'], golden['t_min_in'], 6)
+    assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("stack,brute", [(KO_STACK_T1, KO_BRUTE_T1), (KO_STACK_T2, KO_BRUTE_T2)])
+def test_exact_stack_traversal_equals_brute_force(oracle, golden, stack, brute):
+    tris = golden['tris']
+    canon = canonical_index(tris)
+    for tm in (None, golden['t_min_in']):
+        s = oracle.trace(stack, golden['nodes'], tris, golden['rays'], tm, 6)
+        b = oracle.trace(brute, golden['nodes'], tris, golden['rays'], tm, 6)
+        assert (s['hit'] == b['hit']).all()
+        assert (bits(s['t_min']) == bits(b['t_min'])).all()
+        h = s['hit'] > 0
+        assert (canon[s['tri'][h]] == canon[b['tri'][h]]).all()
+        for k in ('z', 'u', 'v', 'normal'):
+            assert (bits(s[k])[h] == bits(b[k])[h]).all()
+
+
+def test_reference_traversal_loses_hits_only_inside_the_box(oracle, golden_all):
+    """documents the parity contract: T1 == brute force for rays that start outside the root box"""
+    g = golden_all["cornell_dragon_5.npz"]
+    n = (len(g['rays']) * 10) // 21
+    t1 = oracle.trace(KO_T1, g['nodes'], g['tris'], g['rays'][:n], None, 6)
+    b = oracle.trace(KO_BRUTE_T1, g['nodes'], g['tris'], g['rays'][:n], None, 6)
+    assert (t1['hit'] == b['hit']).all() and (bits(t1['t_min']) == bits(b['t_min'])).all()

@@ -1,0 +1,142 @@
+"""GPU parity tests proper: the CUDA kernels, called through the C ABI (libkdpt.so), against the oracle on the same
+seeded inputs and against the reference's own outputs stored in tests/golden. Tolerance: none — hit index, t, z, u, v
+and the normal are compared bit-for-bit (the north star allows 1e-5 relative on t/u/v)."""
+import os
+
+import numpy as np
+import pytest
+
+import kdtreepathtraceroptimization_b200 as kdpt
+from conftest import (GOLDEN, KO_BRUTE_T1, KO_BRUTE_T2, KO_T1, KO_T2, SCENE_FILES, assert_hits_equal, bits, canonical_index)
+
+pytestmark = pytest.mark.gpu
+
+EXACT = [(kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2)]
+REF = [(kdpt.REF_T1, KO_T1, "T1"), (kdpt.REF_T2, KO_T2, "T2")]
+
+
+@pytest.fixture(scope="module", params=SCENE_FILES)
+def scene_ctx(request):
+    path = os.path.join(GOLDEN, request.param)
+    g = np.load(path)
+    ctx = kdpt.Context(kdpt.Scene.from_npz(path))
+    yield g, ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode,omode", EXACT)
+def test_exact_modes_equal_brute_force_oracle(scene_ctx, oracle, mode, omode):
+    g, ctx = scene_ctx
+    for tm in (None, g['t_min_in']):
+        k = ctx.trace(g['rays'], tm, mode)
+        o = oracle.trace(omode, g['nodes'], g['tris'], g['rays'], tm, 6)
+        assert_hits_equal(k, o, g['tris'], f"mode {mode}")
+        assert (k['tri'] >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("mode,omode,name", REF)
+def test_ref_modes_reproduce_the_reference_bit_for_bit(scene_ctx, oracle, mode, omode, name):
+    g, ctx = scene_ctx
+    for sfx, tm in (("", None), ("_tmin", g['t_min_in'])):
+        k = ctx.trace(g['rays'], tm, mode)
+        # the reference's own host functions (golden) ...
+        assert ((k['tri'] >= 0) == (g[f'ref_{name}{sfx}_hit'] > 0)).all()
+        assert (bits(k['t']) == bits(g[f'ref_{name}{sfx}_tmin'])).all()
+        h = k['tri'] >= 0
+        assert (bits(k['normal'])[h] == bits(g[f'ref_{name}{sfx}_normal'])[h]).all()
+        # ... and the oracle for the accepted triangle index and barycentrics
+        assert_hits_equal(k, oracle.trace(omode, g['nodes'], g['tris'], g['rays'], tm, 6), g['tris'], name)
+
+
+def test_exact_equals_reference_where_reference_is_lossless(scene_ctx):
+    """SURVEY §8c contract: equal to the reference's T1 on every ray where T1 itself equals brute force — in
+    particular on all rays starting outside the root box (the first class of the golden ray set)."""
+    g, ctx = scene_ctx
+    n_out = (len(g['rays']) * 10) // 21
+    k = ctx.trace(g['rays'][:n_out], None, kdpt.FULLSTACK)
+    assert ((k['tri'] >= 0) == (g['ref_T1_hit'][:n_out] > 0)).all()
+    assert (bits(k['t']) == bits(g['ref_T1_tmin'][:n_out])).all()
+
+
+def test_ragged_and_empty_batches(scene_ctx, oracle):
+    g, ctx = scene_ctx
+    for n in (0, 1, 31, 33, 127, 1000):
+        k = ctx.trace(g['rays'][:n], None, kdpt.FULLSTACK)
+        assert len(k) == n
+        if n:
+            assert_hits_equal(k, oracle.trace(KO_BRUTE_T1, g['nodes'], g['tris'], g['rays'][:n], None, 6), g['tris'])
+
+
+def test_degenerate_rays_and_empty_tree(oracle):
+    path = os.path.join(GOLDEN, "cornell8_stanford_bunny.npz")
+    g = np.load(path)
+    lo, hi = g['nodes']['mins'][0], g['nodes']['maxs'][0]
+    c = (lo + hi) / 2
+    rays = np.array([[*c, 0, 0, 0], [*c, np.nan, 0, 1], [*c, 1e-30, 0, 0], [*c, 0, 1e30, 0], [*lo, 1, 1, 1], [*hi, -1, -1, -1],
+                     [c[0], c[1], lo[2] - 5, 0, 0, 1], [c[0], c[1], lo[2] - 5, 0, 0, -1], [*c, 0, -0.0, 1]], 'f4')
+    with kdpt.Context(kdpt.Scene.from_npz(path)) as ctx:
+        for mode, om in ((kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2), (kdpt.REF_T1, KO_T1), (kdpt.REF_T2, KO_T2)):
+            assert_hits_equal(ctx.trace(rays, None, mode), oracle.trace(om, g['nodes'], g['tris'], rays, None, 6), g['tris'])
+    with kdpt.Context(kdpt.Scene.tree_only(np.zeros(0, kdpt.NODE), np.zeros(0, kdpt.TRI))) as ctx:
+        k = ctx.trace(g['rays'][:100], None, kdpt.FULLSTACK)
+        assert (k['tri'] == -1).all() and (k['t'] == np.finfo('f4').max).all()
+
+
+def test_tiny_trees(oracle):
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 7):
+        v = rng.uniform(-1, 1, (n, 9)).astype('f4')
+        nr = rng.normal(size=(n, 9)).astype('f4')
+        nodes, tris, _ = oracle.build_tree(np.concatenate([v, nr], 1), None, 13)
+        rays = np.concatenate([rng.uniform(-2, 2, (500, 3)), rng.normal(size=(500, 3))], 1).astype('f4')
+        with kdpt.Context(kdpt.Scene.tree_only(nodes, tris)) as ctx:
+            for mode, om in ((kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2), (kdpt.REF_T1, KO_T1), (kdpt.REF_T2, KO_T2)):
+                assert_hits_equal(ctx.trace(rays, None, mode), oracle.trace(om, nodes, tris, rays, None, 1), tris, f"n={n} mode={mode}")
+
+
+def test_bad_arguments_fail_loudly():
+    path = os.path.join(GOLDEN, "cornell_sphere_low_1.npz")
+    sc = kdpt.Scene.from_npz(path)
+    bad = kdpt.Scene.from_npz(path)
+    bad.nodes = bad.nodes.copy(); bad.nodes['ID'][5] = 99
+    with pytest.raises(kdpt.KdptError, match="ID"):
+        kdpt.Context(bad)
+    with kdpt.Context(sc) as ctx:
+        with pytest.raises(kdpt.KdptError, match="mode"):
+            ctx.trace(np.zeros((4, 6), 'f4'), None, 17)
+    with pytest.raises(kdpt.KdptError, match="device"):
+        kdpt.Context(sc, device=99)
+
+
+def test_large_soup_properties(oracle):
+    """size-independent properties on a tree far beyond the reference's 4000-node limit (its own traversal overflows
+    nodeIDs[4000] there): exact modes agree with each other and with brute force on a sample; every reported hit
+    re-verifies against its own triangle; tracing is idempotent."""
+    rng = np.random.default_rng(12345)
+    n = 200_000
+    c = rng.uniform(-1, 1, (n, 3)); e1 = rng.uniform(-0.02, 0.02, (n, 3)); e2 = rng.uniform(-0.02, 0.02, (n, 3))
+    nrm = np.cross(e1, e2); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    t18 = np.concatenate([c, c + e1, c + e2, nrm, nrm, nrm], 1).astype('f4')
+    nodes, tris, _ = oracle.build_tree(t18, None, 13)
+    assert len(nodes) > 4000
+    lo, hi = nodes['mins'][0], nodes['maxs'][0]
+    m = 1 << 18
+    d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([lo + rng.random((m, 3)) * (hi - lo), d], 1).astype('f4')
+    with kdpt.Context(kdpt.Scene.tree_only(nodes, tris)) as ctx:
+        a = ctx.trace(rays, None, kdpt.FULLSTACK)
+        b = ctx.trace(rays, None, kdpt.FULLSTACK)
+        assert a.tobytes() == b.tobytes()
+        s = ctx.trace(rays, None, kdpt.SHORTSTACK)
+        assert (a['tri'] == s['tri']).all() and (bits(a['z']) == bits(s['z'])).all()
+        k = 4000
+        assert_hits_equal(a[:k], oracle.trace(KO_BRUTE_T1, nodes, tris, rays[:k], None, 1), tris, "soup")
+        h = a['tri'] >= 0
+        assert 0.2 < h.mean() < 1.0
+        # each hit point lies on its triangle's plane and inside it
+        T = tris[a['tri'][h]]
+        v0 = np.stack([T['x1'], T['y1'], T['z1']], 1).astype('f8')
+        e1_ = np.stack([T['x2'], T['y2'], T['z2']], 1) - v0; e2_ = np.stack([T['x3'], T['y3'], T['z3']], 1) - v0
+        p = rays[h, :3].astype('f8') + rays[h, 3:].astype('f8') * a['z'][h, None]
+        q = v0 + e1_ * a['u'][h, None] + e2_ * a['v'][h, None]
+        assert np.abs(p - q).max() < 1e-4
