@@ -27,7 +27,7 @@ else:
     tgt = lo + rng.random((n, 3)) * (hi - lo); d = tgt - o; d /= np.linalg.norm(d, axis=1, keepdims=True)
 rays = torch.from_numpy(np.concatenate([o, d], 1).astype('f4')).cuda()
 hits = torch.zeros(n, 8, dtype=torch.float32, device="cuda")
-st = torch.cuda.current_stream().cuda_stream
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream
 for name in args.modes.split(","):
     m = kdpt.MODES[name]
     ctx.trace_device(rays.data_ptr(), None, n, hits.data_ptr(), m, st)
