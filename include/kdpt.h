@@ -110,10 +110,29 @@ typedef struct {            /* filled by kdpt_render */
     float totalMs;          /* device time of the whole call */
 } kdpt_render_stats;
 
+/* the reference's per-path records, for the stage-level entry points below */
+typedef struct {            /* PathSegment (with its Ray), src/sceneStructs.h:15-20, 65-71 — 56 B */
+    float origin[3], direction[3]; unsigned char isinside, _pad[3]; float sdepth;
+    float color[3]; int pixelIndex, remainingBounces, materialIdHit;
+} kdpt_path_segment;
+typedef struct {            /* ShadeableIntersection, src/sceneStructs.h:81-85 — 20 B */
+    float t; float surfaceNormal[3]; int materialId;
+} kdpt_intersection;
+
+typedef enum {
+    KDPT_STAGE_INTERSECT = 1,   /* pathTraceOneBounceKDbare: geoms + KD traversal + scatterRay, pathtrace.cu:1571-1734 */
+    KDPT_STAGE_SHADE = 2        /* shadeMaterial, pathtrace.cu:2304-2369 */
+} kdpt_stage;
+
 typedef struct kdpt_ctx kdpt_ctx;
 
 int kdpt_abi_version(void);
 const char* kdpt_last_error(void);
+
+/* Host helper: what the reference's main.cpp does to the loaded camera before the first pathtrace() call
+ * (orbit angles from the view vector, main.cpp:1053-1073, then runCuda's recompute of position/view/up/right,
+ * main.cpp:1111-1129). Pure host arithmetic; call it on the camera the scene loader produced. */
+void kdpt_camera_first_frame(kdpt_camera* camera);
 
 /* pathtraceInit: flatten + upload. device = CUDA ordinal. The host arrays are not retained. */
 int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out);
@@ -136,6 +155,13 @@ int kdpt_sync(kdpt_ctx* ctx);
  * the context's radiance buffer. iter_stride > 1 renders iter_begin, iter_begin+stride, ... (sample sharding). */
 int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, const kdpt_params* params,
                 kdpt_render_stats* stats);
+/* stage-level operators on caller-owned HOST arrays in the reference's own layouts (parity tests, integration):
+ * generateRayFromCamera (pathtrace.cu:315-397): W*H segments out */
+int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_path_segment* out);
+/* one bounce over n segments (in/out), `stages` = OR of kdpt_stage; isects (n, may be NULL) receives what the
+ * intersect stage wrote. path_index == array index, as in the reference. */
+int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, kdpt_path_segment* paths, int n,
+                kdpt_intersection* isects, int stages);
 int kdpt_clear_image(kdpt_ctx* ctx);
 /* accumulated radiance, W*H*3 floats (scene->state.image, pathtrace.cu:2631) */
 int kdpt_get_image(kdpt_ctx* ctx, float* rgb);

@@ -27,6 +27,10 @@ MATERIAL = np.dtype([('color', 'f4', 3), ('specular_exponent', 'f4'), ('specular
                      ('hasRefractive', 'f4'), ('indexOfRefraction', 'f4'), ('emittance', 'f4'), ('transmittance', 'f4', 3)])
 CAMERA = np.dtype([('resolution', 'i4', 2), ('position', 'f4', 3), ('lookAt', 'f4', 3), ('view', 'f4', 3), ('up', 'f4', 3),
                    ('right', 'f4', 3), ('fov', 'f4', 2), ('pixelLength', 'f4', 2)])
+PATH = np.dtype([('origin', 'f4', 3), ('direction', 'f4', 3), ('isinside', 'u1'), ('_pad', 'u1', 3), ('sdepth', 'f4'),
+                 ('color', 'f4', 3), ('pixelIndex', 'i4'), ('remainingBounces', 'i4'), ('materialIdHit', 'i4')])
+ISECT = np.dtype([('t', 'f4'), ('surfaceNormal', 'f4', 3), ('materialId', 'i4')])
+STAGE_INTERSECT, STAGE_SHADE = 1, 2
 RAY = np.dtype([('origin', 'f4', 3), ('direction', 'f4', 3)])
 HIT = np.dtype([('t', 'f4'), ('z', 'f4'), ('u', 'f4'), ('v', 'f4'), ('tri', 'i4'), ('normal', 'f4', 3)])
 assert (NODE.itemsize, TRI.itemsize, GEOM.itemsize, MATERIAL.itemsize, CAMERA.itemsize, RAY.itemsize, HIT.itemsize) == \
@@ -96,6 +100,10 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_trace_device.argtypes = [vp, vp, vp, ci, vp, ci, vp]
     lib.kdpt_sync.argtypes = [vp]
     lib.kdpt_render.argtypes = [vp, ci, ci, ci, ctypes.POINTER(CParams), ctypes.POINTER(CRenderStats)]
+    lib.kdpt_generate_rays.argtypes = [vp, ci, ctypes.POINTER(CParams), vp]
+    lib.kdpt_bounce.argtypes = [vp, ci, ci, ctypes.POINTER(CParams), vp, ci, vp, ci]
+    lib.kdpt_camera_first_frame.argtypes = [vp]
+    lib.kdpt_camera_first_frame.restype = None
     lib.kdpt_clear_image.argtypes = [vp]
     lib.kdpt_get_image.argtypes = [vp, vp]
     lib.kdpt_image_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
@@ -130,6 +138,24 @@ class Scene:
                      materials=np.ascontiguousarray(z['materials']), offsets=np.ascontiguousarray(z['offsets'], dtype='i4'),
                      camera=np.ascontiguousarray(z['camera']), trace_depth=int(z['trace_depth']),
                      iterations=int(z['iterations']) if 'iterations' in z else 0)
+
+    def first_frame_camera(self) -> "Scene":
+        """apply the reference's main.cpp camera set-up (kdpt_camera_first_frame) and return self"""
+        cam = np.ascontiguousarray(self.camera.copy())
+        load_library().kdpt_camera_first_frame(cam.ctypes.data_as(ctypes.c_void_p))
+        self.camera = cam
+        return self
+
+    def with_resolution(self, w: int, h: int) -> "Scene":
+        """override RES the way the reference's loader derives pixelLength from it (scene.cpp:216-223)"""
+        cam = self.camera.copy()
+        fovy = np.float32(cam['fov'][0][1])
+        yscaled = np.float32(np.tan(np.float32(fovy * np.float32(np.float32(np.pi) / np.float32(180)))))
+        xscaled = np.float32(np.float32(yscaled * np.float32(w)) / np.float32(h))
+        cam['resolution'][0] = (w, h)
+        cam['pixelLength'][0] = (np.float32(np.float32(2) * xscaled / np.float32(w)), np.float32(np.float32(2) * yscaled / np.float32(h)))
+        self.camera = cam
+        return self
 
     @staticmethod
     def tree_only(nodes: np.ndarray, tris: np.ndarray, num_materials: int = 1) -> "Scene":
@@ -219,6 +245,24 @@ class Context:
         _check(self._lib.kdpt_render(self._h, int(iter_begin), int(iter_count), int(iter_stride), ctypes.byref(p),
                                      ctypes.byref(st)), "kdpt_render")
         return dict(ray_bounces=st.rayBounces, launches=st.launches, intersect_ms=st.intersectMs, total_ms=st.totalMs)
+
+    def generate_rays(self, iteration: int, params: CParams | None = None) -> np.ndarray:
+        p = params if params is not None else default_params()
+        w, h = (int(x) for x in self.scene.camera['resolution'][0])
+        out = np.zeros(w * h, PATH)
+        _check(self._lib.kdpt_generate_rays(self._h, int(iteration), ctypes.byref(p), _ptr(out)), "kdpt_generate_rays")
+        return out
+
+    def bounce(self, iteration: int, depth: int, paths: np.ndarray, stages: int = STAGE_INTERSECT | STAGE_SHADE,
+               isects: np.ndarray | None = None, params: CParams | None = None):
+        """one bounce on caller-owned PathSegment records; returns (paths, intersections)"""
+        p = params if params is not None else default_params()
+        paths = np.ascontiguousarray(paths.copy())
+        assert paths.dtype.itemsize == PATH.itemsize
+        isects = np.zeros(len(paths), ISECT) if isects is None else np.ascontiguousarray(isects.copy())
+        _check(self._lib.kdpt_bounce(self._h, int(iteration), int(depth), ctypes.byref(p), _ptr(paths), len(paths),
+                                     _ptr(isects), int(stages)), "kdpt_bounce")
+        return paths, isects
 
     def clear_image(self):
         _check(self._lib.kdpt_clear_image(self._h), "kdpt_clear_image")

@@ -54,6 +54,34 @@ extern "C" {
 int kdpt_abi_version(void) { return KDPT_ABI_VERSION; }
 const char* kdpt_last_error(void) { return g_lastError.c_str(); }
 
+void kdpt_camera_first_frame(kdpt_camera* cam)
+{
+    if (!cam) return;
+    // separate binary32 operations in glm's order (this file is built with -ffp-contract=off / -fmad=false)
+    auto dot3 = [](const float* a, const float* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; };
+    auto norm3 = [&](const float* a, float* o) { float s = 1.0f / sqrtf(dot3(a, a)); o[0] = a[0] * s; o[1] = a[1] * s; o[2] = a[2] * s; };
+    auto cross3 = [](const float* x, const float* y, float* o) {
+        float r0 = x[1] * y[2] - y[1] * x[2], r1 = x[2] * y[0] - y[2] * x[0], r2 = x[0] * y[1] - y[0] * x[1];
+        o[0] = r0; o[1] = r1; o[2] = r2;
+    };
+    float viewXZ[3] = {cam->view[0], 0.0f, cam->view[2]}, viewZY[3] = {0.0f, cam->view[1], cam->view[2]};
+    float nxz[3], nzy[3];
+    norm3(viewXZ, nxz); norm3(viewZY, nzy);
+    const float fwd[3] = {0, 0, -1}, upAxis[3] = {0, 1, 0};
+    float phi = acosf(dot3(nxz, fwd));
+    float theta = acosf(dot3(nzy, upAxis));
+    float dlt[3] = {cam->position[0] - cam->lookAt[0], cam->position[1] - cam->lookAt[1], cam->position[2] - cam->lookAt[2]};
+    float zoom = sqrtf(dot3(dlt, dlt));
+    float cp[3] = {zoom * sinf(phi) * sinf(theta) + 0.f, zoom * cosf(theta) + 0.f, zoom * cosf(phi) * sinf(theta) + 0.f};
+    float n[3]; norm3(cp, n);
+    float v[3] = {-n[0], -n[1], -n[2]}, r[3], u[3];
+    cross3(v, upAxis, r); cross3(r, v, u);
+    for (int k = 0; k < 3; k++) {
+        cam->view[k] = v[k]; cam->up[k] = u[k]; cam->right[k] = r[k];
+        cam->position[k] = cp[k] + (cam->lookAt[k] + 0.f);
+    }
+}
+
 int kdpt_destroy(kdpt_ctx* ctx)
 {
     if (!ctx) return KDPT_OK;

@@ -1,9 +1,650 @@
-// placeholder until the render loop lands
+// kdpt_render.cu — the render loop (sm_100a): generate rays -> [intersect+scatter+shade+gather -> compact -> sort]* ->
+// accumulate. Replaces pathtrace() and its kernels (src/pathtrace.cu:315-397, 1571-1734, 2304-2399, 2405-2635) and
+// the thrust::remove_if / thrust::sort calls (2591-2606).
+//
+// Design (B200-first, not the reference's):
+//  * path state is SoA (3 x float4 + int2 = 56 B/path) instead of the 56-B AoS PathSegment, so every access is a
+//    coalesced 128-bit load/store;
+//  * one fused persistent kernel per bounce does what the reference spreads over cudaMemset + intersect + shade +
+//    partialGather, and leaves a per-packet survivor count for the compaction;
+//  * nothing in an iteration needs the host: path counts live in device memory (np[bounce]), kernels are launched
+//    with a fixed persistent grid, so an iteration is a fixed launch sequence with no cudaDeviceSynchronize, no
+//    per-bounce cudaMemset of 20 B x pixels and no per-iteration D2H image copy (the reference has all three);
+//  * stream compaction = warp-ballot prefix sums (packet counts -> one-block scan -> stable scatter), the material
+//    sort = hand-written stable LSD radix sort (8-bit digits) on materialIdHit. No thrust.
+//  * the per-iteration camera jitter, which the reference recomputes identically in every pixel thread
+//    (RNG seeded by utilhash(iter) only, pathtrace.cu:334), is computed once per iteration on the host.
 #include "kdpt_internal.h"
-using namespace kdpt;
-extern "C" {
-int kdpt_render(kdpt_ctx*, int, int, int, const kdpt_params*, kdpt_render_stats*) { setError("kdpt_render: not built"); return KDPT_ERR_STATE; }
-int kdpt_clear_image(kdpt_ctx*) { setError("not built"); return KDPT_ERR_STATE; }
-int kdpt_get_image(kdpt_ctx*, float*) { setError("not built"); return KDPT_ERR_STATE; }
-int kdpt_image_device(kdpt_ctx*, float**, int*) { setError("not built"); return KDPT_ERR_STATE; }
+#include "kdpt_render.cuh"
+#include <string.h>
+
+namespace kdpt {
+
+constexpr int kThreads = 128;
+constexpr int kMaxBounces = 8;          // the reference's hard cap `depth > 7`, pathtrace.cu:2608
+constexpr int kMaxSmemGeoms = 32;
+constexpr int kSortTile = 512;
+
+struct PathSoA {
+    float4* od;   // origin.xyz, sdepth
+    float4* dr;   // direction.xyz, isinside (0/1 as float)
+    float4* cp;   // color.rgb, pixelIndex (int bits)
+    int2* bm;     // remainingBounces, materialIdHit
+};
+
+// per-iteration constants of generateRayFromCamera (pathtrace.cu:333-389), identical for every pixel
+struct IterConst {
+    int iter; int antialias;
+    float jx, jy, jz;          // normalised jitter vector (scaled by 0.002 in the kernel)
+    float qw, qx, qy, qz;      // DOF rotation quaternion
+};
+
+struct LoopState {
+    int np[kMaxBounces + 2];                 // live paths at the start of each bounce
+    unsigned ticket[4 * (kMaxBounces + 1)];  // packet counters: [b] bounce kernel, [9+b] compaction, [18+b]/[27+b] sort
+    unsigned long long bounceRays[kMaxBounces];
+};
+
+struct SceneView {
+    const kdpt_geom* geoms; int numGeoms;
+    const kdpt_material* materials; int numMaterials;
+};
+
+struct BounceArgs {
+    int iter, depth, stages;    // stages: kdpt_stage bits; 4 = gather finished paths into the image (compaction on)
+    float softness; int enableSss;
+    float eps;
+};
+
+__host__ __device__ inline unsigned hUtilhash(unsigned a)
+{
+    a = (a + 0x7ed55d16) + (a << 12);
+    a = (a ^ 0xc761c23c) ^ (a >> 19);
+    a = (a + 0x165667b1) + (a << 5);
+    a = (a + 0xd3a2646c) ^ (a << 9);
+    a = (a + 0xfd7046c5) + (a << 3);
+    a = (a ^ 0xb55a4f09) ^ (a >> 16);
+    return a;
 }
+struct HostRng {
+    unsigned x;
+    void seed(unsigned s) { unsigned v = s % 2147483647u; x = v == 0 ? 1u : v; }
+    float u01()
+    {
+        x = (unsigned)(((unsigned long long)x * 48271ull) % 2147483647ull);
+        float r = (float)(x - 1u);
+        r /= (1.0f + (float)(2147483646u - 1u));
+        return (r * (1.0f - 0.0f)) + 0.0f;
+    }
+};
+
+// host: the iteration-constant part of generateRayFromCamera (compiled with -ffp-contract=off)
+static IterConst makeIterConst(int iter, const kdpt_params& p)
+{
+    IterConst c; memset(&c, 0, sizeof c);
+    c.iter = iter; c.antialias = p.antialias;
+    HostRng rng; rng.seed(hUtilhash((unsigned)iter));
+    if (p.antialias) {
+        float a = rng.u01(), b = rng.u01(), cc = rng.u01();
+        float s = 1.0f / sqrtf((a * a + b * b) + cc * cc);
+        c.jx = a * s; c.jy = b * s; c.jz = cc * s;
+    }
+    float u = cosf(KDPT_PI * rng.u01());
+    float u2 = u * u;
+    float s1 = sqrtf(1 - u2);
+    float theta = 2 * KDPT_PI * rng.u01();
+    float vx = s1 * cosf(theta), vy = s1 * sinf(theta), vz = u;
+    float s = 1.0f / sqrtf((vx * vx + vy * vy) + vz * vz);
+    vx = vx * s; vy = vy * s; vz = vz * s;
+    (void)rng.u01(); (void)rng.u01();
+    float randangle = rng.u01() * KDPT_PI * p.dofAngle;
+    float sh = sinf(randangle / 2.0f);
+    c.qw = cosf(randangle / 2.0f); c.qx = vx * sh; c.qy = vy * sh; c.qz = vz * sh;
+    return c;
+}
+
+// ---- generateRayFromCamera ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+generateRaysKernel(kdpt_camera cam, IterConst ic, int traceDepth, float focal, PathSoA P, LoopState* st)
+{
+    int n = cam.resolution[0] * cam.resolution[1];
+    int index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (index == 0) {
+        st->np[0] = n;
+        for (int k = 0; k < 4 * (kMaxBounces + 1); k++) st->ticket[k] = 0;
+    }
+    if (index >= n) return;
+    int W = cam.resolution[0], H = cam.resolution[1];
+    int x = index % W, y = index / W;
+    V3 view = mk(cam.view[0], cam.view[1], cam.view[2]), right = mk(cam.right[0], cam.right[1], cam.right[2]);
+    V3 up = mk(cam.up[0], cam.up[1], cam.up[2]), pos = mk(cam.position[0], cam.position[1], cam.position[2]);
+    V3 dir = normalize((view - (right * cam.pixelLength[0]) * ((float)x - (float)W * 0.5f)) -
+                       (up * cam.pixelLength[1]) * ((float)y - (float)H * 0.5f));
+    if (ic.antialias) {
+        dir = dir + mk(ic.jx, ic.jy, ic.jz) * 0.002f;
+        dir = normalize(dir);
+    }
+    V3 qv = mk(ic.qx, ic.qy, ic.qz);
+    V3 uv = cross(qv, dir), uuv = cross(qv, uv);
+    V3 rot = dir + ((uv * ic.qw) + uuv) * 2.0f;
+    V3 org = (pos + dir * focal) - rot * focal;
+    dir = normalize(rot);
+    P.od[index] = make_float4(org.x, org.y, org.z, 0.0f);
+    P.dr[index] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+    P.cp[index] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(index));
+    P.bm[index] = make_int2(traceDepth, 0);
+}
+
+// ---- one bounce: intersect (+scatter) + shade + gather, persistent warps pulling 32-path packets ------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, float* __restrict__ image,
+             int* __restrict__ packetCount, kdpt_intersection* __restrict__ isectOut)
+{
+    __shared__ kdpt_geom sGeoms[kMaxSmemGeoms];
+    const int ng = S.numGeoms < kMaxSmemGeoms ? S.numGeoms : kMaxSmemGeoms;
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(S.geoms);
+        unsigned* dst = reinterpret_cast<unsigned*>(sGeoms);
+        for (int k = threadIdx.x; k < ng * (int)(sizeof(kdpt_geom) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    const int n = st->np[A.depth];
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long liveLocal = 0;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&st->ticket[A.depth], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned)n) break;
+        unsigned i = base + lane;
+        bool alive = false, live = false;
+        if (i < (unsigned)n) {
+            int2 bm = P.bm[i];
+            int remaining = bm.x;
+            if (remaining > 0) {
+                live = true;
+                float4 od = P.od[i], dr = P.dr[i], cp = P.cp[i];
+                PathRay r; r.o = mk(od.x, od.y, od.z); r.d = mk(dr.x, dr.y, dr.z); r.inside = dr.w != 0.0f; r.sdepth = od.w;
+                V3 color = mk(cp.x, cp.y, cp.z);
+                float t = 0.0f; int matId = 0; V3 normal = mk(0, 0, 0);   // dev_intersections is memset to 0 per bounce
+                if (A.stages & KDPT_STAGE_INTERSECT) {
+                    float tMin = FLT_MAX; int hitGeom = -1; V3 ipoint = mk(0, 0, 0);
+                    for (int g = 0; g < S.numGeoms; g++) {
+                        V3 pt, nr;
+                        float tg = g < ng ? geomTest(sGeoms[g], r.o, r.d, pt, nr) : geomTest(S.geoms[g], r.o, r.d, pt, nr);
+                        if (tg > 0.0f && tMin > tg) { tMin = tg; hitGeom = g; ipoint = pt; normal = nr; }
+                    }
+                    Hit H;
+                    if (MODE == KDPT_FULLSTACK) traceExact<kMaxDepth, false>(T, r.o, r.d, tMin, 0.00001f, H, nullptr);
+                    else if (MODE == KDPT_SHORTSTACK) traceExact<4, false>(T, r.o, r.d, tMin, 0.0001f, H, nullptr);
+                    else if (MODE == KDPT_REF_T1) traceRef<false>(T, r.o, r.d, tMin, H, nullptr);
+                    else traceRef<true>(T, r.o, r.d, tMin, H, nullptr);
+                    bool objHit = H.tri >= 0;
+                    if (objHit) {
+                        // the reference's nudged point: o + d*z + n*eps (pathtrace.cu:993-995)
+                        normal = mk(H.nx, H.ny, H.nz);
+                        ipoint = (r.o + r.d * H.z) + normal * A.eps;
+                        tMin = H.t;
+                        // reference: material of the LAST triangle glm accepted (pathtrace.cu:991); exact modes: of the hit
+                        int mtl = (MODE == KDPT_REF_T1 || MODE == KDPT_REF_T2) ? H.anyMtl : H.mtl;
+                        matId = mtl + T.materialSize - 1;
+                    } else if (hitGeom >= 0) matId = S.geoms[hitGeom].materialid;
+                    // multi-shape OBJs index past materials[] in the reference (Appendix A #5); stay in bounds here
+                    matId = matId < 0 ? 0 : (matId >= S.numMaterials ? S.numMaterials - 1 : matId);
+                    if (!objHit && hitGeom < 0) t = -1.0f;          // pathtrace.cu:1683-1686
+                    else {
+                        const kdpt_material m = S.materials[matId];
+                        scatterRay(r, ipoint, normal, m, pathSeed(A.iter, (int)i, A.depth), A.softness);
+                        t = tMin;
+                        bm.y = matId;
+                    }
+                    if (isectOut) {
+                        kdpt_intersection is; is.t = t; is.surfaceNormal[0] = t == -1.0f ? 0.f : normal.x;
+                        is.surfaceNormal[1] = t == -1.0f ? 0.f : normal.y; is.surfaceNormal[2] = t == -1.0f ? 0.f : normal.z;
+                        is.materialId = t == -1.0f ? 0 : matId;
+                        isectOut[i] = is;
+                    }
+                } else if (isectOut) {      // shade-only call: the caller supplies the intersections
+                    kdpt_intersection is = isectOut[i];
+                    t = is.t; matId = is.materialId;
+                }
+                if (A.stages & KDPT_STAGE_SHADE) {
+                    if (t > 0.0f) remaining = shadeHit(S.materials[matId], A.enableSss != 0, r.sdepth, color, remaining);
+                    else { color = mk(0, 0, 0); remaining = 0; }
+                }
+                if ((A.stages & 4) && remaining == 0) {     // partialGather: one live path per pixel, no atomics needed
+                    int pix = __float_as_int(cp.w);
+                    float* px = image + 3 * (size_t)pix;
+                    px[0] += color.x; px[1] += color.y; px[2] += color.z;
+                }
+                P.od[i] = make_float4(r.o.x, r.o.y, r.o.z, r.sdepth);
+                P.dr[i] = make_float4(r.d.x, r.d.y, r.d.z, r.inside ? 1.0f : 0.0f);
+                P.cp[i] = make_float4(color.x, color.y, color.z, cp.w);
+                bm.x = remaining;
+                P.bm[i] = bm;
+            }
+            alive = remaining > 0;
+        }
+        unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
+        unsigned liveMask = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) {
+            if (packetCount) packetCount[base >> 5] = __popc(aliveMask);
+            liveLocal += (unsigned)__popc(liveMask);
+        }
+    }
+    if (lane == 0 && liveLocal && A.depth < kMaxBounces) atomicAdd(&st->bounceRays[A.depth], liveLocal);
+}
+
+// ---- stream compaction (replaces thrust::remove_if, pathtrace.cu:2591-2597) ---------------------------------------
+// packetCount[k] = survivors in paths [32k, 32k+32). One block turns them into exclusive offsets and publishes the
+// next bounce's path count.
+__global__ void __launch_bounds__(1024)
+scanPacketsKernel(int* __restrict__ packetCount, LoopState* st, int depth, int compaction)
+{
+    __shared__ int warpSums[32];
+    __shared__ int carry;
+    const int n = st->np[depth];
+    if (!compaction) { if (threadIdx.x == 0) st->np[depth + 1] = n; return; }
+    const int numPackets = (n + 31) >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < numPackets; base += 1024) {
+        int k = base + threadIdx.x;
+        int v = k < numPackets ? packetCount[k] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warpSums[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += t; }
+            warpSums[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        int excl = carry + warpSums[threadIdx.x >> 5] + incl - v;
+        if (k < numPackets) packetCount[k] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st->np[depth + 1] = carry;
+}
+
+__global__ void __launch_bounds__(kThreads)
+compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset, LoopState* st, int depth)
+{
+    const int n = st->np[depth];
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&st->ticket[9 + depth], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned)n) break;
+        unsigned i = base + lane;
+        int2 bm = make_int2(0, 0);
+        if (i < (unsigned)n) bm = P.bm[i];
+        bool alive = i < (unsigned)n && bm.x != 0;          // is_zero_bounce, pathtrace.cu:103-110
+        unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (alive) {
+            int dst = packetOffset[base >> 5] + __popc(mask & ((1u << lane) - 1u));
+            Q.od[dst] = P.od[i]; Q.dr[dst] = P.dr[i]; Q.cp[dst] = P.cp[i]; Q.bm[dst] = bm;
+        }
+    }
+}
+
+// ---- stable LSD radix sort by materialIdHit (replaces thrust::sort, pathtrace.cu:2600-2606) -----------------------
+__device__ __forceinline__ unsigned sortDigit(int materialIdHit, int shift) { return ((unsigned)(materialIdHit + 1) >> shift) & 255u; }
+
+__global__ void __launch_bounds__(kSortTile)
+sortHistKernel(PathSoA P, LoopState* st, int depth, int shift, unsigned* __restrict__ hist, int maxTiles)
+{
+    __shared__ unsigned h[256];
+    const int n = st->np[depth];
+    const int numTiles = (n + kSortTile - 1) / kSortTile;
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        if (threadIdx.x < 256) h[threadIdx.x] = 0;
+        __syncthreads();
+        int i = tile * kSortTile + threadIdx.x;
+        if (i < n) atomicAdd(&h[sortDigit(P.bm[i].y, shift)], 1u);
+        __syncthreads();
+        if (threadIdx.x < 256) hist[threadIdx.x * maxTiles + tile] = h[threadIdx.x];
+        __syncthreads();
+    }
+}
+// exclusive scan over (digit-major, tile-minor) counts; one block
+__global__ void __launch_bounds__(1024)
+sortScanKernel(LoopState* st, int depth, unsigned* __restrict__ hist, int maxTiles)
+{
+    __shared__ unsigned warpSums[32];
+    __shared__ unsigned carry;
+    const int n = st->np[depth];
+    const int numTiles = (n + kSortTile - 1) / kSortTile;
+    const int total = 256 * numTiles;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += 1024) {
+        int k = base + threadIdx.x;
+        int digit = k / numTiles, tile = k - digit * numTiles;
+        unsigned v = k < total ? hist[digit * maxTiles + tile] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = warpSums[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += t; }
+            warpSums[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        unsigned excl = carry + warpSums[threadIdx.x >> 5] + incl - v;
+        if (k < total) hist[digit * maxTiles + tile] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kSortTile)
+sortScatterKernel(PathSoA P, PathSoA Q, LoopState* st, int depth, int shift, const unsigned* __restrict__ hist, int maxTiles)
+{
+    __shared__ unsigned short warpDigitCount[kSortTile / 32][256];
+    const int n = st->np[depth];
+    const int numTiles = (n + kSortTile - 1) / kSortTile;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        for (int k = threadIdx.x; k < (kSortTile / 32) * 256; k += blockDim.x) (&warpDigitCount[0][0])[k] = 0;
+        __syncthreads();
+        int i = tile * kSortTile + threadIdx.x;
+        bool valid = i < n;
+        int2 bm = valid ? P.bm[i] : make_int2(0, 0);
+        unsigned digit = valid ? sortDigit(bm.y, shift) : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) warpDigitCount[warp][digit] = (unsigned short)__popc(peers);
+        __syncthreads();
+        if (valid) {
+            unsigned dst = hist[digit * maxTiles + tile] + rank;
+            for (unsigned w = 0; w < warp; w++) dst += warpDigitCount[w][digit];
+            Q.od[dst] = P.od[i]; Q.dr[dst] = P.dr[i]; Q.cp[dst] = P.cp[i]; Q.bm[dst] = bm;
+        }
+        __syncthreads();
+    }
+}
+
+// finalGather (compaction off), pathtrace.cu:2373-2383: every path adds its colour
+__global__ void finalGatherKernel(PathSoA P, LoopState* st, int depth, float* __restrict__ image)
+{
+    const int n = st->np[depth];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 cp = P.cp[i];
+        float* px = image + 3 * (size_t)__float_as_int(cp.w);
+        px[0] += cp.x; px[1] += cp.y; px[2] += cp.z;
+    }
+}
+
+// AoS <-> SoA for the stage-level entry points
+__global__ void packPathsKernel(const kdpt_path_segment* __restrict__ in, int n, PathSoA P, LoopState* st, int depth)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { st->np[depth] = n; st->ticket[depth] = 0; }
+    if (i >= n) return;
+    kdpt_path_segment s = in[i];
+    P.od[i] = make_float4(s.origin[0], s.origin[1], s.origin[2], s.sdepth);
+    P.dr[i] = make_float4(s.direction[0], s.direction[1], s.direction[2], s.isinside ? 1.0f : 0.0f);
+    P.cp[i] = make_float4(s.color[0], s.color[1], s.color[2], __int_as_float(s.pixelIndex));
+    P.bm[i] = make_int2(s.remainingBounces, s.materialIdHit);
+}
+__global__ void unpackPathsKernel(PathSoA P, int n, kdpt_path_segment* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 od = P.od[i], dr = P.dr[i], cp = P.cp[i]; int2 bm = P.bm[i];
+    kdpt_path_segment s; memset(&s, 0, sizeof s);
+    s.origin[0] = od.x; s.origin[1] = od.y; s.origin[2] = od.z; s.sdepth = od.w;
+    s.direction[0] = dr.x; s.direction[1] = dr.y; s.direction[2] = dr.z; s.isinside = dr.w != 0.0f;
+    s.color[0] = cp.x; s.color[1] = cp.y; s.color[2] = cp.z; s.pixelIndex = __float_as_int(cp.w);
+    s.remainingBounces = bm.x; s.materialIdHit = bm.y;
+    out[i] = s;
+}
+
+// ---- host driver --------------------------------------------------------------------------------------------------
+struct RenderBuffers {
+    PathSoA A, B;
+    LoopState* st;
+    int* packetCount;
+    unsigned* hist; int maxTiles;
+    float* image;
+};
+
+static int ensureRenderBuffers(kdpt_ctx* ctx, int n, RenderBuffers& rb)
+{
+    int rc;
+    size_t per = sizeof(float4) * 3 + sizeof(int2);
+    if ((rc = ctx->pathsA.ensure(per * (size_t)n)) || (rc = ctx->pathsB.ensure(per * (size_t)n))) return rc;
+    auto carve = [&](DeviceBuffer& b, PathSoA& P) {
+        char* p = (char*)b.p;
+        size_t cap = b.bytes / per;
+        P.od = (float4*)p; P.dr = (float4*)(p + sizeof(float4) * cap); P.cp = (float4*)(p + 2 * sizeof(float4) * cap);
+        P.bm = (int2*)(p + 3 * sizeof(float4) * cap);
+    };
+    carve(ctx->pathsA, rb.A); carve(ctx->pathsB, rb.B);
+    bool fresh = ctx->scanTmp.p == nullptr;
+    if ((rc = ctx->scanTmp.ensure(sizeof(LoopState)))) return rc;
+    if (fresh) KDPT_CUDA(cudaMemsetAsync(ctx->scanTmp.p, 0, sizeof(LoopState), ctx->stream));
+    rb.st = ctx->scanTmp.as<LoopState>();
+    if ((rc = ctx->keysTmp.ensure(sizeof(int) * (size_t)((n + 31) / 32 + 1)))) return rc;
+    rb.packetCount = ctx->keysTmp.as<int>();
+    rb.maxTiles = (n + kSortTile - 1) / kSortTile + 1;
+    if ((rc = ctx->hist.ensure(sizeof(unsigned) * 256 * (size_t)rb.maxTiles))) return rc;
+    rb.hist = ctx->hist.as<unsigned>();
+    rb.image = ctx->image.as<float>();
+    return KDPT_OK;
+}
+
+static int ensureImage(kdpt_ctx* ctx)
+{
+    if (!ctx->scene.hasCamera) { setError("render: the scene has no camera (resolution 0)"); return KDPT_ERR_STATE; }
+    int n = ctx->scene.camera.resolution[0] * ctx->scene.camera.resolution[1];
+    if (ctx->image.p && ctx->pixelCount == n) return KDPT_OK;
+    int rc = ctx->image.alloc(sizeof(float) * 3 * (size_t)n);
+    if (rc) return rc;
+    ctx->pixelCount = n;
+    KDPT_CUDA(cudaMemsetAsync(ctx->image.p, 0, sizeof(float) * 3 * (size_t)n, ctx->stream));
+    return KDPT_OK;
+}
+
+static int checkParams(const kdpt_params* p)
+{
+    if (!p) { setError("render: null params"); return KDPT_ERR_ARG; }
+    if (p->mode < 0 || p->mode >= KDPT_MODE_COUNT) { setError("render: unknown traversal mode"); return KDPT_ERR_ARG; }
+    if (p->sortByMaterial < 0 || p->sortByMaterial > 2) { setError("render: sortByMaterial must be 0, 1 or 2"); return KDPT_ERR_ARG; }
+    return KDPT_OK;
+}
+
+static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers& rb, PathSoA P, int iter, int depth,
+                        int stages, kdpt_intersection* dIsects, uint64_t& launches)
+{
+    SceneView S{ctx->scene.geoms.as<kdpt_geom>(), ctx->scene.numGeoms, ctx->scene.materials.as<kdpt_material>(), ctx->scene.numMaterials};
+    BounceArgs A; A.iter = iter; A.depth = depth; A.stages = stages; A.softness = p.softness; A.enableSss = p.enableSss;
+    A.eps = (p.mode == KDPT_SHORTSTACK || p.mode == KDPT_REF_T2) ? 0.0001f : 0.00001f;
+    int grid = ctx->numSMs * 8;
+    cudaStream_t s = ctx->stream;
+    int* pc = p.compaction ? rb.packetCount : nullptr;
+    switch (p.mode) {
+    case KDPT_FULLSTACK: bounceKernel<KDPT_FULLSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
+    case KDPT_SHORTSTACK: bounceKernel<KDPT_SHORTSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
+    case KDPT_REF_T1: bounceKernel<KDPT_REF_T1><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
+    default: bounceKernel<KDPT_REF_T2><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
+    }
+    launches++;
+    KDPT_CUDA(cudaGetLastError());
+    return KDPT_OK;
+}
+
+} // namespace kdpt
+
+using namespace kdpt;
+
+extern "C" {
+
+int kdpt_clear_image(kdpt_ctx* ctx)
+{
+    if (!ctx) { setError("kdpt_clear_image: null context"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensureImage(ctx);
+    if (rc) return rc;
+    KDPT_CUDA(cudaMemsetAsync(ctx->image.p, 0, sizeof(float) * 3 * (size_t)ctx->pixelCount, ctx->stream));
+    return KDPT_OK;
+}
+
+int kdpt_get_image(kdpt_ctx* ctx, float* rgb)
+{
+    if (!ctx || !rgb) { setError("kdpt_get_image: null argument"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensureImage(ctx);
+    if (rc) return rc;
+    KDPT_CUDA(cudaMemcpyAsync(rgb, ctx->image.p, sizeof(float) * 3 * (size_t)ctx->pixelCount, cudaMemcpyDeviceToHost, ctx->stream));
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KDPT_OK;
+}
+
+int kdpt_image_device(kdpt_ctx* ctx, float** d_rgb, int* numFloats)
+{
+    if (!ctx || !d_rgb) { setError("kdpt_image_device: null argument"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensureImage(ctx);
+    if (rc) return rc;
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    *d_rgb = ctx->image.as<float>();
+    if (numFloats) *numFloats = 3 * ctx->pixelCount;
+    return KDPT_OK;
+}
+
+int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, const kdpt_params* params, kdpt_render_stats* stats)
+{
+    if (!ctx || iter_count < 0 || iter_stride < 1) { setError("kdpt_render: bad argument"); return KDPT_ERR_ARG; }
+    int rc = checkParams(params);
+    if (rc) return rc;
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ensureImage(ctx))) return rc;
+    const kdpt_params& p = *params;
+    const int n = ctx->pixelCount;
+    RenderBuffers rb;
+    if ((rc = ensureRenderBuffers(ctx, n, rb))) return rc;
+    cudaStream_t s = ctx->stream;
+    uint64_t launches = 0;
+    unsigned long long before[kMaxBounces], after[kMaxBounces];
+    KDPT_CUDA(cudaMemcpyAsync(before, rb.st->bounceRays, sizeof before, cudaMemcpyDeviceToHost, s));
+    KDPT_CUDA(cudaEventRecord(ctx->ev0, s));
+    const int grid = ctx->numSMs * 8;
+    int sortPasses = 1;
+    for (int m = ctx->scene.numMaterials + 1; m > 256; m >>= 8) sortPasses++;
+    for (int k = 0; k < iter_count; k++) {
+        const int iter = iter_begin + k * iter_stride;
+        IterConst ic = makeIterConst(iter, p);
+        generateRaysKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ic, ctx->scene.traceDepth, p.focalLength, rb.A, rb.st);
+        launches++;
+        PathSoA cur = rb.A, other = rb.B;
+        const bool sortThis = p.sortByMaterial == 2 || (p.sortByMaterial == 1 && iter == 2);
+        int depth = 0;
+        // remainingBounces starts at traceDepth and drops every bounce, so nothing survives min(8, traceDepth) bounces
+        const int maxBounces = ctx->scene.traceDepth < kMaxBounces ? (ctx->scene.traceDepth < 0 ? 0 : ctx->scene.traceDepth) : kMaxBounces;
+        for (; depth < maxBounces; depth++) {
+            int stages = KDPT_STAGE_INTERSECT | KDPT_STAGE_SHADE | (p.compaction ? 4 : 0);
+            if ((rc = launchBounce(ctx, p, rb, cur, iter, depth, stages, nullptr, launches))) return rc;
+            scanPacketsKernel<<<1, 1024, 0, s>>>(rb.packetCount, rb.st, depth, p.compaction);
+            launches++;
+            if (p.compaction) {
+                compactScatterKernel<<<grid, kThreads, 0, s>>>(cur, other, rb.packetCount, rb.st, depth);
+                launches++;
+                PathSoA t = cur; cur = other; other = t;
+            }
+            if (sortThis) {
+                for (int pass = 0; pass < sortPasses; pass++) {
+                    sortHistKernel<<<grid, kSortTile, 0, s>>>(cur, rb.st, depth + 1, 8 * pass, rb.hist, rb.maxTiles);
+                    sortScanKernel<<<1, 1024, 0, s>>>(rb.st, depth + 1, rb.hist, rb.maxTiles);
+                    sortScatterKernel<<<grid, kSortTile, 0, s>>>(cur, other, rb.st, depth + 1, 8 * pass, rb.hist, rb.maxTiles);
+                    launches += 3;
+                    PathSoA t = cur; cur = other; other = t;
+                }
+            }
+        }
+        if (!p.compaction) {
+            finalGatherKernel<<<grid, 256, 0, s>>>(cur, rb.st, maxBounces, rb.image);
+            launches++;
+        }
+        KDPT_CUDA(cudaGetLastError());
+    }
+    KDPT_CUDA(cudaEventRecord(ctx->ev1, s));
+    KDPT_CUDA(cudaMemcpyAsync(after, rb.st->bounceRays, sizeof after, cudaMemcpyDeviceToHost, s));
+    KDPT_CUDA(cudaStreamSynchronize(s));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int b = 0; b < kMaxBounces; b++) stats->rayBounces += after[b] - before[b];
+        stats->launches = launches;
+        KDPT_CUDA(cudaEventElapsedTime(&stats->totalMs, ctx->ev0, ctx->ev1));
+        stats->intersectMs = 0.0f;
+    }
+    return KDPT_OK;
+}
+
+int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_path_segment* out)
+{
+    if (!ctx || !out) { setError("kdpt_generate_rays: null argument"); return KDPT_ERR_ARG; }
+    int rc = checkParams(params);
+    if (rc) return rc;
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ensureImage(ctx))) return rc;
+    const int n = ctx->pixelCount;
+    RenderBuffers rb;
+    if ((rc = ensureRenderBuffers(ctx, n, rb))) return rc;
+    if ((rc = ctx->isects.ensure(sizeof(kdpt_path_segment) * (size_t)n))) return rc;
+    cudaStream_t s = ctx->stream;
+    IterConst ic = makeIterConst(iter, *params);
+    generateRaysKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ic, ctx->scene.traceDepth, params->focalLength, rb.A, rb.st);
+    unpackPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(rb.A, n, ctx->isects.as<kdpt_path_segment>());
+    KDPT_CUDA(cudaGetLastError());
+    KDPT_CUDA(cudaMemcpyAsync(out, ctx->isects.p, sizeof(kdpt_path_segment) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    KDPT_CUDA(cudaStreamSynchronize(s));
+    return KDPT_OK;
+}
+
+int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, kdpt_path_segment* paths, int n,
+                kdpt_intersection* isects, int stages)
+{
+    if (!ctx || n < 0 || (n > 0 && !paths) || depth < 0 || depth >= kMaxBounces || (stages & ~3) || !stages) {
+        setError("kdpt_bounce: bad argument");
+        return KDPT_ERR_ARG;
+    }
+    if (stages == KDPT_STAGE_SHADE && !isects) { setError("kdpt_bounce: the shade stage alone needs the intersections"); return KDPT_ERR_ARG; }
+    int rc = checkParams(params);
+    if (rc) return rc;
+    if (n == 0) return KDPT_OK;
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    RenderBuffers rb;
+    if ((rc = ensureRenderBuffers(ctx, n, rb))) return rc;
+    size_t pb = sizeof(kdpt_path_segment) * (size_t)n, ib = sizeof(kdpt_intersection) * (size_t)n;
+    if ((rc = ctx->isects.ensure(pb + ib))) return rc;
+    kdpt_path_segment* dPaths = ctx->isects.as<kdpt_path_segment>();
+    kdpt_intersection* dIs = (kdpt_intersection*)((char*)ctx->isects.p + pb);
+    cudaStream_t s = ctx->stream;
+    KDPT_CUDA(cudaMemcpyAsync(dPaths, paths, pb, cudaMemcpyHostToDevice, s));
+    if (isects && stages == KDPT_STAGE_SHADE) KDPT_CUDA(cudaMemcpyAsync(dIs, isects, ib, cudaMemcpyHostToDevice, s));
+    else KDPT_CUDA(cudaMemsetAsync(dIs, 0, ib, s));
+    packPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(dPaths, n, rb.A, rb.st, depth);
+    kdpt_params p = *params; p.compaction = 0;
+    uint64_t launches = 0;
+    if ((rc = launchBounce(ctx, p, rb, rb.A, iter, depth, stages, dIs, launches))) return rc;
+    unpackPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(rb.A, n, dPaths);
+    KDPT_CUDA(cudaGetLastError());
+    KDPT_CUDA(cudaMemcpyAsync(paths, dPaths, pb, cudaMemcpyDeviceToHost, s));
+    if (isects) KDPT_CUDA(cudaMemcpyAsync(isects, dIs, ib, cudaMemcpyDeviceToHost, s));
+    KDPT_CUDA(cudaStreamSynchronize(s));
+    return KDPT_OK;
+}
+
+} // extern "C"

@@ -107,3 +107,47 @@ def assert_hits_equal(kh, oh, tris, what=""):
     for k in ('z', 'u', 'v'):
         assert (bits(oh[k])[h] == bits(kh[k])[h]).all(), f"{what}: {k} differs"
     assert (bits(oh['normal'])[h] == bits(kh['normal'])[h]).all(), f"{what}: normal differs"
+
+
+# ---- oracle render-loop helpers -----------------------------------------------------------------------------------
+class KoCamera(ctypes.Structure):
+    _fields_ = [("res", ctypes.c_int * 2), ("position", ctypes.c_float * 3), ("lookAt", ctypes.c_float * 3),
+                ("view", ctypes.c_float * 3), ("up", ctypes.c_float * 3), ("right", ctypes.c_float * 3),
+                ("fov", ctypes.c_float * 2), ("pixelLength", ctypes.c_float * 2)]
+
+
+class KoScene(ctypes.Structure):
+    _fields_ = [("nodes", ctypes.c_void_p), ("numNodes", ctypes.c_int), ("tris", ctypes.c_void_p), ("numTris", ctypes.c_int),
+                ("geoms", ctypes.c_void_p), ("numGeoms", ctypes.c_int), ("mats", ctypes.c_void_p), ("numMats", ctypes.c_int),
+                ("cam", KoCamera)]
+
+
+class KoRenderParams(ctypes.Structure):
+    _fields_ = [("focalLength", ctypes.c_float), ("dofAngle", ctypes.c_float), ("softness", ctypes.c_float),
+                ("antialias", ctypes.c_int), ("enableSss", ctypes.c_int), ("compaction", ctypes.c_int),
+                ("shortstack", ctypes.c_int), ("sortMode", ctypes.c_int), ("traceDepth", ctypes.c_int)]
+
+
+KO_PATH = np.dtype([('origin', 'f4', 3), ('direction', 'f4', 3), ('isinside', 'u1'), ('_pad', 'u1', 3), ('sdepth', 'f4'),
+                    ('color', 'f4', 3), ('pixelIndex', 'i4'), ('remainingBounces', 'i4'), ('materialIdHit', 'i4')])
+KO_ISECT = np.dtype([('t', 'f4'), ('normal', 'f4', 3), ('materialId', 'i4')])
+# kdpt_mode -> oracle traversal mode / ko_render_params.shortstack
+KDPT_TO_KO = {0: KO_STACK_T1, 1: KO_STACK_T2, 2: KO_T1, 3: KO_T2}
+KDPT_TO_KO_SHORTSTACK = {0: 2, 1: 3, 2: 0, 3: 1}
+
+
+def ko_scene(scene):
+    """scene: kdtreepathtraceroptimization_b200.Scene (arrays are kept alive by the caller)"""
+    s = KoScene()
+    s.nodes, s.numNodes = scene.nodes.ctypes.data, len(scene.nodes)
+    s.tris, s.numTris = scene.tris.ctypes.data, len(scene.tris)
+    s.geoms, s.numGeoms = (scene.geoms.ctypes.data if len(scene.geoms) else None), len(scene.geoms)
+    s.mats, s.numMats = scene.materials.ctypes.data, len(scene.materials)
+    ctypes.memmove(ctypes.byref(s.cam), scene.camera.ctypes.data, 84)
+    return s
+
+
+def ko_params(p, trace_depth):
+    """kdpt CParams -> ko_render_params"""
+    return KoRenderParams(p.focalLength, p.dofAngle, p.softness, p.antialias, p.enableSss, p.compaction,
+                          KDPT_TO_KO_SHORTSTACK[p.mode], p.sortByMaterial, trace_depth)

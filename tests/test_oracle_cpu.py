@@ -126,3 +126,62 @@ def test_reference_traversal_loses_hits_only_inside_the_box(oracle, golden_all):
     t1 = oracle.trace(KO_T1, g['nodes'], g['tris'], g['rays'][:n], None, 6)
     b = oracle.trace(KO_BRUTE_T1, g['nodes'], g['tris'], g['rays'][:n], None, 6)
     assert (t1['hit'] == b['hit']).all() and (bits(t1['t_min']) == bits(b['t_min'])).all()
+
+
+# ---- render-loop pieces -----------------------------------------------------------------------------------------
+KO_GEOM = np.dtype([('type', 'i4'), ('materialid', 'i4'), ('translation', 'f4', 3), ('rotation', 'f4', 3), ('scale', 'f4', 3),
+                    ('transform', 'f4', 16), ('inverseTransform', 'f4', 16), ('invTranspose', 'f4', 16)])
+KO_PATH = np.dtype([('origin', 'f4', 3), ('direction', 'f4', 3), ('isinside', 'u1'), ('_pad', 'u1', 3), ('sdepth', 'f4'),
+                    ('color', 'f4', 3), ('pixelIndex', 'i4'), ('remainingBounces', 'i4'), ('materialIdHit', 'i4')])
+assert KO_PATH.itemsize == 56
+
+
+def test_rng_matches_thrust_minstd(oracle, golden):
+    """makeSeededRandomEngine + uniform_real_distribution<float> (pathtrace.cu:62-66; thrust minstd_rand)"""
+    oracle.lib.ko_seed.restype = ctypes.c_uint
+    for (it, ix, dp), draws, seed in zip(golden['rng_query'], golden['rng_draws'], golden['rng_seed']):
+        s = oracle.lib.ko_seed(int(it), int(ix), int(dp))
+        assert s == int(seed)
+        out = np.zeros(12, 'f4')
+        oracle.lib.ko_rng_draws(ctypes.c_uint(s), 12, P(out))
+        assert (bits(out) == bits(draws)).all()
+
+
+def test_analytic_geoms_match_reference(oracle, golden):
+    """boxIntersectionTest / sphereIntersectionTest (intersections.h:107-203)"""
+    oracle.lib.ko_geom_test.restype = ctypes.c_float
+    geoms, rays = golden['geoms'], golden['geom_rays']
+    nhit = 0
+    for g in range(len(geoms)):
+        for i in range(0, len(rays), 3):
+            pt = np.zeros(3, 'f4'); nr = np.zeros(3, 'f4'); outside = ctypes.c_int(1)
+            t = oracle.lib.ko_geom_test(P(geoms[g:g + 1]), P(rays[i, :3].copy()), P(rays[i, 3:].copy()), P(pt), P(nr), ctypes.byref(outside))
+            assert bits(np.float32(t)) == bits(golden['geom_t'][g, i])
+            if t > 0:
+                nhit += 1
+                assert (bits(pt) == bits(golden['geom_point'][g, i])).all()
+                assert (bits(nr) == bits(golden['geom_normal'][g, i])).all()
+                assert outside.value == golden['geom_outside'][g, i]
+    assert nhit > 40
+
+
+def test_scatter_matches_reference(oracle, golden):
+    """scatterRay (interactions.h:195-358) on every scene material + synthetic mirror / glass / SSS materials, with and
+    without softness; same glibc on both sides, so bit-for-bit"""
+    oracle.lib.ko_seed.restype = ctypes.c_uint
+    oracle.lib.ko_scatter.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint, ctypes.c_float]
+    mats = golden['scatter_mats']
+    k = 0
+    for mi in range(len(mats)):
+        for soft in (0.0, 0.3):
+            rin, pts, nrm = golden['scatter_in_rays'][k], golden['scatter_in_points'][k], golden['scatter_in_normals'][k]
+            rout = golden['scatter_out_rays'][k]
+            for i in range(0, len(rin), 2):
+                p = np.zeros(1, KO_PATH)
+                p['origin'] = rin[i, :3]; p['direction'] = rin[i, 3:6]; p['isinside'] = int(rin[i, 6] != 0); p['sdepth'] = rin[i, 7]
+                seed = oracle.lib.ko_seed(7, 1000 * mi + i, 3)
+                oracle.lib.ko_scatter(P(p), P(pts[i].copy()), P(nrm[i].copy()), P(mats[mi:mi + 1]), seed, soft)
+                got = np.concatenate([p['origin'][0], p['direction'][0], [np.float32(p['isinside'][0])], [p['sdepth'][0]]]).astype('f4')
+                ok = (bits(got) == bits(rout[i])) | (np.isnan(got) & np.isnan(rout[i]))
+                assert ok.all(), (mi, soft, i, got, rout[i])
+            k += 1
