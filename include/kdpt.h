@@ -100,7 +100,9 @@ typedef struct {
     int compaction;         /* default 1 */
     int mode;               /* kdpt_mode; the reference's SHORTSTACK=true is KDPT_REF_T2, false KDPT_REF_T1 */
     int sortByMaterial;     /* 0 never, 1 only in iteration 2 (reference, pathtrace.cu:2600), 2 every bounce */
-    int reserved[4];
+    int testingmode;        /* TESTINGMODE (pathtrace.cu:2478-2481, 2565-2574): time every intersect kernel with CUDA
+                               events and report the sum in kdpt_render_stats.intersectMs */
+    int reserved[3];
 } kdpt_params;
 
 typedef struct {            /* filled by kdpt_render */
@@ -154,7 +156,7 @@ int kdpt_sync(kdpt_ctx* ctx);
 /* pathtrace(): iterations iter_begin .. iter_begin+iter_count-1 (the reference counts from 1), accumulating into
  * the context's radiance buffer. iter_stride > 1 renders iter_begin, iter_begin+stride, ... (sample sharding). */
 int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, const kdpt_params* params,
-                kdpt_render_stats* stats);
+                kdpt_render_stats* stats /* NULL: enqueue only, do not synchronise */);
 /* stage-level operators on caller-owned HOST arrays in the reference's own layouts (parity tests, integration):
  * generateRayFromCamera (pathtrace.cu:315-397): W*H segments out */
 int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_path_segment* out);
@@ -163,6 +165,13 @@ int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_
 int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, kdpt_path_segment* paths, int n,
                 kdpt_intersection* isects, int stages);
 int kdpt_clear_image(kdpt_ctx* ctx);
+/* Run all of this context's work on the caller's stream (a cudaStream_t; NULL restores the context's own stream). */
+int kdpt_set_stream(kdpt_ctx* ctx, void* stream);
+/* Accumulate radiance into a caller-owned DEVICE buffer of W*H*3 floats (e.g. the tensor an NCCL all-reduce runs
+ * on); NULL goes back to the context's own buffer. The buffer is not cleared. */
+int kdpt_bind_image(kdpt_ctx* ctx, float* d_rgb);
+/* cumulative since kdpt_create: ray-bounces traced by the render loop and kernels launched (synchronises) */
+int kdpt_counters(kdpt_ctx* ctx, uint64_t* rayBounces, uint64_t* launches);
 /* accumulated radiance, W*H*3 floats (scene->state.image, pathtrace.cu:2631) */
 int kdpt_get_image(kdpt_ctx* ctx, float* rgb);
 /* device pointer of that buffer (for an NCCL all-reduce issued by the caller) */

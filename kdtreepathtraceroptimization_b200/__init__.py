@@ -61,7 +61,8 @@ class CParams(ctypes.Structure):
     """kdpt_params — the trailing arguments of the reference's pathtrace() (defaults main.cpp:35-60)."""
     _fields_ = [("focalLength", ctypes.c_float), ("dofAngle", ctypes.c_float), ("softness", ctypes.c_float),
                 ("antialias", ctypes.c_int), ("enableSss", ctypes.c_int), ("compaction", ctypes.c_int),
-                ("mode", ctypes.c_int), ("sortByMaterial", ctypes.c_int), ("reserved", ctypes.c_int * 4)]
+                ("mode", ctypes.c_int), ("sortByMaterial", ctypes.c_int), ("testingmode", ctypes.c_int),
+                ("reserved", ctypes.c_int * 3)]
 
 
 class CRenderStats(ctypes.Structure):
@@ -105,6 +106,9 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_camera_first_frame.argtypes = [vp]
     lib.kdpt_camera_first_frame.restype = None
     lib.kdpt_clear_image.argtypes = [vp]
+    lib.kdpt_set_stream.argtypes = [vp, vp]
+    lib.kdpt_bind_image.argtypes = [vp, vp]
+    lib.kdpt_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     lib.kdpt_get_image.argtypes = [vp, vp]
     lib.kdpt_image_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
     if lib.kdpt_abi_version() != 1:
@@ -238,6 +242,23 @@ class Context:
 
     def sync(self):
         _check(self._lib.kdpt_sync(self._h), "kdpt_sync")
+
+    def set_stream(self, stream: int | None):
+        _check(self._lib.kdpt_set_stream(self._h, stream), "kdpt_set_stream")
+
+    def bind_image(self, d_rgb: int | None):
+        _check(self._lib.kdpt_bind_image(self._h, d_rgb), "kdpt_bind_image")
+
+    def counters(self) -> tuple[int, int]:
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        _check(self._lib.kdpt_counters(self._h, ctypes.byref(a), ctypes.byref(b)), "kdpt_counters")
+        return a.value, b.value
+
+    def render_async(self, iter_begin: int, iter_count: int, iter_stride: int = 1, params: CParams | None = None):
+        """enqueue only (stats == NULL): no host synchronisation"""
+        p = params if params is not None else default_params()
+        _check(self._lib.kdpt_render(self._h, int(iter_begin), int(iter_count), int(iter_stride), ctypes.byref(p), None),
+               "kdpt_render")
 
     def render(self, iter_begin: int, iter_count: int, iter_stride: int = 1, params: CParams | None = None) -> dict:
         p = params if params is not None else default_params()

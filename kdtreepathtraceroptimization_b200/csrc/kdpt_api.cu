@@ -87,6 +87,7 @@ int kdpt_destroy(kdpt_ctx* ctx)
     if (!ctx) return KDPT_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->eventPool) cudaEventDestroy(e);
     for (auto& b : ctx->treeMem) b.release();
     DeviceBuffer* bufs[] = {&ctx->scene.geoms, &ctx->scene.materials, &ctx->scene.offsets, &ctx->rays, &ctx->tmin,
                             &ctx->hits, &ctx->counter, &ctx->image, &ctx->pathsA, &ctx->pathsB, &ctx->isects,
@@ -96,7 +97,7 @@ int kdpt_destroy(kdpt_ctx* ctx)
     if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);
     cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev2, ctx->ev3};
     for (auto e : evs) if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     delete ctx;
     return KDPT_OK;
 }
@@ -131,7 +132,8 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(cudaFail(e, "cudaGetDeviceProperties"));
     ctx->numSMs = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaFail(e, "cudaStreamCreate"));
+    if ((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaFail(e, "cudaStreamCreate"));
+    ctx->stream = ctx->ownStream;
     cudaEvent_t* evs[] = {&ctx->ev0, &ctx->ev1, &ctx->ev2, &ctx->ev3};
     for (auto pe : evs) if ((e = cudaEventCreate(pe)) != cudaSuccess) return fail(cudaFail(e, "cudaEventCreate"));
 
@@ -186,6 +188,15 @@ int kdpt_tree_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* ma
     return KDPT_OK;
 }
 
+int kdpt_set_stream(kdpt_ctx* ctx, void* stream)
+{
+    if (!ctx) { setError("kdpt_set_stream: null context"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->ownStream;
+    return KDPT_OK;
+}
+
 int kdpt_sync(kdpt_ctx* ctx)
 {
     if (!ctx) { setError("kdpt_sync: null context"); return KDPT_ERR_ARG; }
@@ -199,6 +210,7 @@ int kdpt_trace_device(kdpt_ctx* ctx, const kdpt_ray* d_rays, const float* d_t_mi
     if (!ctx || n < 0 || (n > 0 && (!d_rays || !d_hits))) { setError("kdpt_trace_device: bad argument"); return KDPT_ERR_ARG; }
     if (mode < 0 || mode >= KDPT_MODE_COUNT) { setError("kdpt_trace_device: unknown mode"); return KDPT_ERR_ARG; }
     KDPT_CUDA(cudaSetDevice(ctx->device));
+    ctx->launches++;
     return launchTrace(ctx, d_rays, d_t_min_in, n, d_hits, mode, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
@@ -216,6 +228,7 @@ int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n
     KDPT_CUDA(cudaMemcpyAsync(ctx->rays.p, rays, rb, cudaMemcpyHostToDevice, s));
     if (t_min_in) KDPT_CUDA(cudaMemcpyAsync(ctx->tmin.p, t_min_in, tb, cudaMemcpyHostToDevice, s));
     if ((rc = launchTrace(ctx, ctx->rays.as<kdpt_ray>(), t_min_in ? ctx->tmin.as<float>() : nullptr, n, ctx->hits.as<kdpt_hit>(), mode, s))) return rc;
+    ctx->launches++;
     KDPT_CUDA(cudaMemcpyAsync(hits, ctx->hits.p, hb, cudaMemcpyDeviceToHost, s));
     KDPT_CUDA(cudaStreamSynchronize(s));
     return KDPT_OK;

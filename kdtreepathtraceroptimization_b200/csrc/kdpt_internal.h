@@ -54,6 +54,10 @@ struct kdpt_ctx {
     // render loop state
     kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist;
     int pixelCount = 0;
+    float* boundImage = nullptr;        // caller-owned radiance buffer (kdpt_bind_image)
+    cudaStream_t ownStream = nullptr;   // `stream` may point at a caller's stream (kdpt_set_stream)
+    uint64_t launches = 0;              // kernels launched so far
+    std::vector<cudaEvent_t> eventPool; // TESTINGMODE event pairs
 };
 
 namespace kdpt {

@@ -441,7 +441,7 @@ static int ensureRenderBuffers(kdpt_ctx* ctx, int n, RenderBuffers& rb)
     rb.maxTiles = (n + kSortTile - 1) / kSortTile + 1;
     if ((rc = ctx->hist.ensure(sizeof(unsigned) * 256 * (size_t)rb.maxTiles))) return rc;
     rb.hist = ctx->hist.as<unsigned>();
-    rb.image = ctx->image.as<float>();
+    rb.image = ctx->boundImage ? ctx->boundImage : ctx->image.as<float>();
     return KDPT_OK;
 }
 
@@ -497,7 +497,7 @@ int kdpt_clear_image(kdpt_ctx* ctx)
     KDPT_CUDA(cudaSetDevice(ctx->device));
     int rc = ensureImage(ctx);
     if (rc) return rc;
-    KDPT_CUDA(cudaMemsetAsync(ctx->image.p, 0, sizeof(float) * 3 * (size_t)ctx->pixelCount, ctx->stream));
+    KDPT_CUDA(cudaMemsetAsync(ctx->boundImage ? (void*)ctx->boundImage : ctx->image.p, 0, sizeof(float) * 3 * (size_t)ctx->pixelCount, ctx->stream));
     return KDPT_OK;
 }
 
@@ -507,8 +507,36 @@ int kdpt_get_image(kdpt_ctx* ctx, float* rgb)
     KDPT_CUDA(cudaSetDevice(ctx->device));
     int rc = ensureImage(ctx);
     if (rc) return rc;
-    KDPT_CUDA(cudaMemcpyAsync(rgb, ctx->image.p, sizeof(float) * 3 * (size_t)ctx->pixelCount, cudaMemcpyDeviceToHost, ctx->stream));
+    KDPT_CUDA(cudaMemcpyAsync(rgb, ctx->boundImage ? (void*)ctx->boundImage : ctx->image.p, sizeof(float) * 3 * (size_t)ctx->pixelCount, cudaMemcpyDeviceToHost, ctx->stream));
     KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KDPT_OK;
+}
+
+int kdpt_bind_image(kdpt_ctx* ctx, float* d_rgb)
+{
+    if (!ctx) { setError("kdpt_bind_image: null context"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensureImage(ctx);
+    if (rc) return rc;
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->boundImage = d_rgb;
+    return KDPT_OK;
+}
+
+int kdpt_counters(kdpt_ctx* ctx, uint64_t* rayBounces, uint64_t* launches)
+{
+    if (!ctx) { setError("kdpt_counters: null context"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    if (launches) *launches = ctx->launches;
+    if (rayBounces) {
+        *rayBounces = 0;
+        if (ctx->scanTmp.p) {
+            unsigned long long c[kMaxBounces];
+            KDPT_CUDA(cudaMemcpyAsync(c, ctx->scanTmp.as<LoopState>()->bounceRays, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+            KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int b = 0; b < kMaxBounces; b++) *rayBounces += c[b];
+        }
+    }
     return KDPT_OK;
 }
 
@@ -519,7 +547,7 @@ int kdpt_image_device(kdpt_ctx* ctx, float** d_rgb, int* numFloats)
     int rc = ensureImage(ctx);
     if (rc) return rc;
     KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
-    *d_rgb = ctx->image.as<float>();
+    *d_rgb = ctx->boundImage ? ctx->boundImage : ctx->image.as<float>();
     if (numFloats) *numFloats = 3 * ctx->pixelCount;
     return KDPT_OK;
 }
@@ -538,8 +566,15 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     cudaStream_t s = ctx->stream;
     uint64_t launches = 0;
     unsigned long long before[kMaxBounces], after[kMaxBounces];
-    KDPT_CUDA(cudaMemcpyAsync(before, rb.st->bounceRays, sizeof before, cudaMemcpyDeviceToHost, s));
-    KDPT_CUDA(cudaEventRecord(ctx->ev0, s));
+    if (stats) KDPT_CUDA(cudaMemcpyAsync(before, rb.st->bounceRays, sizeof before, cudaMemcpyDeviceToHost, s));
+    if (stats) KDPT_CUDA(cudaEventRecord(ctx->ev0, s));
+    const bool timing = stats && p.testingmode;
+    size_t evUsed = 0;
+    auto nextEvent = [&](cudaEvent_t& e) -> int {
+        if (evUsed == ctx->eventPool.size()) { cudaEvent_t ne; KDPT_CUDA(cudaEventCreate(&ne)); ctx->eventPool.push_back(ne); }
+        e = ctx->eventPool[evUsed++];
+        return KDPT_OK;
+    };
     const int grid = ctx->numSMs * 8;
     int sortPasses = 1;
     for (int m = ctx->scene.numMaterials + 1; m > 256; m >>= 8) sortPasses++;
@@ -555,7 +590,10 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
         const int maxBounces = ctx->scene.traceDepth < kMaxBounces ? (ctx->scene.traceDepth < 0 ? 0 : ctx->scene.traceDepth) : kMaxBounces;
         for (; depth < maxBounces; depth++) {
             int stages = KDPT_STAGE_INTERSECT | KDPT_STAGE_SHADE | (p.compaction ? 4 : 0);
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (timing) { if ((rc = nextEvent(t0)) || (rc = nextEvent(t1))) return rc; KDPT_CUDA(cudaEventRecord(t0, s)); }
             if ((rc = launchBounce(ctx, p, rb, cur, iter, depth, stages, nullptr, launches))) return rc;
+            if (timing) KDPT_CUDA(cudaEventRecord(t1, s));
             scanPacketsKernel<<<1, 1024, 0, s>>>(rb.packetCount, rb.st, depth, p.compaction);
             launches++;
             if (p.compaction) {
@@ -579,15 +617,21 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
         }
         KDPT_CUDA(cudaGetLastError());
     }
-    KDPT_CUDA(cudaEventRecord(ctx->ev1, s));
-    KDPT_CUDA(cudaMemcpyAsync(after, rb.st->bounceRays, sizeof after, cudaMemcpyDeviceToHost, s));
-    KDPT_CUDA(cudaStreamSynchronize(s));
+    ctx->launches += launches;
     if (stats) {
+        KDPT_CUDA(cudaEventRecord(ctx->ev1, s));
+        KDPT_CUDA(cudaMemcpyAsync(after, rb.st->bounceRays, sizeof after, cudaMemcpyDeviceToHost, s));
+        KDPT_CUDA(cudaStreamSynchronize(s));
         memset(stats, 0, sizeof *stats);
         for (int b = 0; b < kMaxBounces; b++) stats->rayBounces += after[b] - before[b];
         stats->launches = launches;
         KDPT_CUDA(cudaEventElapsedTime(&stats->totalMs, ctx->ev0, ctx->ev1));
         stats->intersectMs = 0.0f;
+        for (size_t k = 0; k + 1 < evUsed; k += 2) {
+            float ms = 0.f;
+            KDPT_CUDA(cudaEventElapsedTime(&ms, ctx->eventPool[k], ctx->eventPool[k + 1]));
+            stats->intersectMs += ms;
+        }
     }
     return KDPT_OK;
 }

@@ -17,6 +17,9 @@
 #include <cfloat>
 #include <cstring>
 #include <cstdio>
+#include <thread>
+#include <chrono>
+#include <algorithm>
 
 #include "pathtrace.cu"    // resolved through -I/root/reference/src
 
@@ -201,6 +204,128 @@ int kdref_soup_tree_dump(const char* soup_path, int maxdepth, const char* out_pa
     T->split(maxdepth);
     T->writeKDtoFile(T->rootNode, out_path);
     return 0;
+}
+
+// ---- CPU baseline: the reference's own host functions driven by a host-side harness ---------------------------
+// One iteration of the render loop on the host cores. The per-path work is the reference's code, called unmodified:
+// boxIntersectionTest / sphereIntersectionTest (intersections.h), traverseKDbare / traverseKDbareShortHybrid
+// (pathtrace.cu:881-1235), makeSeededRandomEngine + scatterRay (interactions.h). The loop around them follows
+// pathTraceOneBounceKDbare (1571-1734), shadeMaterial (2304-2369), partialGather, remove_if and the bounce cap of
+// pathtrace() (2405-2635); those are __global__ kernels / thrust calls in the reference and cannot run on a host, so
+// the harness states their few lines of glue here. paths: W*H PathSegment (generated by the caller), consumed.
+// Returns the number of ray-bounces traced; seconds[0] = intersect stage, seconds[1] = everything else.
+static void kdref_intersect_range(int lo, int hi, int depth, int iter, PathSegment* paths, Geom* geoms, int geoms_size,
+                                  Material* materials, int material_size, ShadeableIntersection* intersections,
+                                  float softness, KDN::TriBare* triangles, KDN::NodeBare* nodes, int numNodes,
+                                  int* offsets, bool shortstack)
+{
+    for (int path_index = lo; path_index < hi; path_index++) {
+        PathSegment pathSegment = paths[path_index];
+        if (paths[path_index].remainingBounces <= 0) continue;
+        float t = 0.f, t_min = FLT_MAX;
+        glm::vec3 intersect_point, normal, tmp_intersect, tmp_normal, hit, norm, bary;
+        int hit_geom_index = -1, objMaterialIdx = -1;
+        bool outside = true, obj_intersect = false;
+        for (int i = 0; i < geoms_size; i++) {
+            Geom& geom = geoms[i];
+            if (geom.type == CUBE) t = boxIntersectionTest(geom, pathSegment.ray, tmp_intersect, tmp_normal, outside);
+            else if (geom.type == SPHERE) t = sphereIntersectionTest(geom, pathSegment.ray, tmp_intersect, tmp_normal, outside);
+            if (t > 0.0f && t_min > t) { t_min = t; hit_geom_index = i; intersect_point = tmp_intersect; normal = tmp_normal; }
+        }
+        if (numNodes > 0) {
+            if (!shortstack)
+                traverseKDbare(nodes, numNodes, t, pathSegment, triangles, bary, objMaterialIdx, material_size, hit, norm,
+                               t_min, hit_geom_index, intersect_point, normal, tmp_intersect, tmp_normal, obj_intersect,
+                               intersections, offsets, path_index);
+            else
+                traverseKDbareShortHybrid(nodes, numNodes, t, pathSegment, triangles, bary, objMaterialIdx, material_size,
+                                          hit, norm, t_min, hit_geom_index, intersect_point, normal, tmp_intersect,
+                                          tmp_normal, obj_intersect, intersections, offsets, path_index);
+        }
+        if (hit_geom_index == -1) { intersections[path_index].t = -1.0f; continue; }
+        thrust::default_random_engine rng = makeSeededRandomEngine(iter, path_index, depth);
+        int mat = obj_intersect ? objMaterialIdx : geoms[hit_geom_index].materialid;
+        paths[path_index].materialIdHit = mat;
+        scatterRay(paths[path_index].ray, paths[path_index].color, intersect_point, normal, materials[mat], rng, softness);
+        intersections[path_index].t = t_min;
+        intersections[path_index].materialId = mat;
+        intersections[path_index].surfaceNormal = normal;
+    }
+}
+
+long kdref_cpu_iteration(const void* nodes_, int numNodes, const void* tris_, const void* geoms_, int geoms_size,
+                         const void* mats_, int material_size, const int* offsets, void* paths_, int pixelcount,
+                         int iter, float softness, int enableSss, int compaction, int shortstack, int sortmode,
+                         float* image /* pixelcount*3, += */, int nthreads, double* seconds)
+{
+    KDN::NodeBare* nodes = (KDN::NodeBare*)nodes_; KDN::TriBare* tris = (KDN::TriBare*)tris_;
+    Geom* geoms = (Geom*)geoms_; Material* materials = (Material*)mats_;
+    PathSegment* paths = (PathSegment*)paths_;
+    std::vector<ShadeableIntersection> isects(pixelcount);
+    int num_paths = pixelcount, depth = 0;
+    long total = 0;
+    double tIsect = 0, tRest = 0;
+    if (nthreads < 1) nthreads = 1;
+    for (;;) {
+        auto c0 = std::chrono::steady_clock::now();
+        memset(isects.data(), 0, sizeof(ShadeableIntersection) * pixelcount);
+        std::vector<std::thread> th;
+        for (int k = 0; k < nthreads; k++) {
+            int lo = (int)((long)num_paths * k / nthreads), hi = (int)((long)num_paths * (k + 1) / nthreads);
+            th.emplace_back(kdref_intersect_range, lo, hi, depth, iter, paths, geoms, geoms_size, materials, material_size,
+                            isects.data(), softness, tris, nodes, numNodes, (int*)offsets, shortstack != 0);
+        }
+        for (auto& t : th) t.join();
+        auto c1 = std::chrono::steady_clock::now();
+        for (int i = 0; i < num_paths; i++) total += paths[i].remainingBounces > 0;
+        depth++;
+        for (int idx = 0; idx < num_paths; idx++) {                      // shadeMaterial
+            PathSegment& ps = paths[idx];
+            if (ps.remainingBounces <= 0) continue;
+            ShadeableIntersection is = isects[idx];
+            if (is.t > 0.0f) {
+                Material material = materials[is.materialId];
+                glm::vec3 materialColor = material.color;
+                if (material.emittance > 0.0f) { ps.color *= (materialColor * material.emittance); ps.remainingBounces = 0; }
+                else {
+                    if (enableSss && (material.transmittance.x > 0.0f || material.transmittance.y > 0.0f || material.transmittance.z > 0.0f)) {
+                        float scenescale = 1.0f;
+                        float sss = scenescale * ps.ray.sdepth > 1.0 ? 1.0 : ps.ray.sdepth;
+                        sss = 1.0f - sss < 0.0 ? 0.0 : sss;
+                        sss = glm::pow(sss, 2);
+                        ps.color *= (materialColor)* 1.0f + material.hasRefractive * material.specular.color + sss * material.transmittance;
+                    }
+                    else if (material.hasRefractive > 0.0f) ps.color *= (materialColor)* 1.0f + material.hasRefractive * material.specular.color;
+                    else if (material.hasReflective > 0.0f) ps.color *= (materialColor)* 1.0f + material.hasReflective * material.specular.color;
+                    else ps.color *= (materialColor) * 1.0f;
+                    ps.remainingBounces--;
+                }
+            } else { ps.color = glm::vec3(0.0f); ps.remainingBounces = 0; }
+        }
+        if (compaction) {
+            for (int i = 0; i < num_paths; i++)
+                if (paths[i].remainingBounces == 0) {
+                    int px = paths[i].pixelIndex;
+                    image[3 * px] += paths[i].color.x; image[3 * px + 1] += paths[i].color.y; image[3 * px + 2] += paths[i].color.z;
+                }
+            int k = 0;
+            for (int i = 0; i < num_paths; i++) if (paths[i].remainingBounces != 0) paths[k++] = paths[i];
+            num_paths = k;
+        }
+        if (sortmode == 2 || (sortmode == 1 && iter == 2))
+            std::stable_sort(paths, paths + num_paths, [](const PathSegment& a, const PathSegment& b) { return a.materialIdHit < b.materialIdHit; });
+        auto c2 = std::chrono::steady_clock::now();
+        tIsect += std::chrono::duration<double>(c1 - c0).count();
+        tRest += std::chrono::duration<double>(c2 - c1).count();
+        if (num_paths <= 0 || depth > 7) break;
+    }
+    if (!compaction)
+        for (int i = 0; i < num_paths; i++) {
+            int idx = paths[i].pixelIndex; PathSegment p = paths[idx];
+            image[3 * p.pixelIndex] += p.color.x; image[3 * p.pixelIndex + 1] += p.color.y; image[3 * p.pixelIndex + 2] += p.color.z;
+        }
+    if (seconds) { seconds[0] = tIsect; seconds[1] = tRest; }
+    return total;
 }
 
 // ---- GPU-only: the reference's own render loop on whatever CUDA device is present -------------

@@ -34,6 +34,7 @@ class Oracle:
         if hasattr(lib, "ko_render_iteration"):
             lib.ko_render_iteration.restype = ctypes.c_long
             lib.ko_collect_bounce_rays.restype = ctypes.c_long
+            lib.ko_render_iteration_counted.restype = ctypes.c_long
 
     def trace(self, mode, nodes, tris, rays, t_min_in=None, material_size=1, nthreads=8, counters=False):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)

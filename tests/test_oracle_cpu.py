@@ -185,3 +185,35 @@ def test_scatter_matches_reference(oracle, golden):
                 ok = (bits(got) == bits(rout[i])) | (np.isnan(got) & np.isnan(rout[i]))
                 assert ok.all(), (mi, soft, i, got, rout[i])
             k += 1
+
+
+def test_render_loop_matches_reference_host_harness(oracle):
+    """Whole-iteration pin: the oracle's pathtrace() restatement vs the harness in oracle/ref_shim.cu that drives the
+    reference's OWN host functions (geoms, traverseKDbare/ShortHybrid, makeSeededRandomEngine, scatterRay). Same
+    glibc on both sides -> bit-identical radiance. Needs oracle/_ref/libkdref.so (built where /root/reference
+    exists; it ships to the GPU box as a prebuilt file)."""
+    import kdtreepathtraceroptimization_b200 as kdpt
+    from conftest import ROOT, KO_PATH as KP, ko_params, ko_scene
+    so = os.path.join(ROOT, "oracle", "_ref", "libkdref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libkdref.so not built")
+    R = ctypes.CDLL(so)
+    R.kdref_cpu_iteration.restype = ctypes.c_long
+    for name, mode, sortmode in (("cornell8_stanford_bunny.npz", kdpt.REF_T1, 1), ("cornell_sphere_low_1.npz", kdpt.REF_T2, 1)):
+        sc = kdpt.Scene.from_npz(os.path.join(GOLDEN, name)).with_resolution(96, 96)
+        cam = sc.camera.copy(); oracle.lib.ko_camera_runcuda(P(cam)); sc.camera = cam
+        p = kdpt.default_params(mode=mode, sortByMaterial=sortmode)
+        ks = ko_scene(sc); kp = ko_params(p, sc.trace_depth)
+        n = 96 * 96
+        for it in (1, 2):
+            img_o = np.zeros((n, 3), 'f4')
+            tot_o = oracle.lib.ko_render_iteration(ctypes.byref(ks), ctypes.byref(kp), it, P(img_o), None, 4)
+            paths = np.zeros(n, KP)
+            oracle.lib.ko_generate_rays(ctypes.byref(ks.cam), it, sc.trace_depth, ctypes.c_float(p.focalLength),
+                                        ctypes.c_float(p.dofAngle), p.antialias, P(paths))
+            img_r = np.zeros((n, 3), 'f4'); secs = np.zeros(2, 'f8')
+            tot_r = R.kdref_cpu_iteration(P(sc.nodes), len(sc.nodes), P(sc.tris), P(sc.geoms), len(sc.geoms), P(sc.materials),
+                                          len(sc.materials), P(sc.offsets), P(paths), n, it, ctypes.c_float(0.0), 0, 1,
+                                          1 if mode == kdpt.REF_T2 else 0, sortmode, P(img_r), 4, P(secs))
+            assert tot_o == tot_r and tot_o > n
+            assert (bits(img_o) == bits(img_r)).all()
