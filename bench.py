@@ -293,8 +293,12 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         c2 = kdpt.Context(hsc, device=local)
+        t1 = time.perf_counter()
         st = c2.render(1 + k * S * world + rank, S, world, params)
+        t2 = time.perf_counter()
         kdpt._check(lib.kdpt_get_image(c2._h, ctypes.c_void_p(himg.data_ptr())), "kdpt_get_image")
+        if rank == 0 and os.environ.get("KDPT_BENCH_DEBUG"):
+            print(f"e2e step {k}: create {1e3 * (t1 - t0):.2f} ms, render {1e3 * (t2 - t1):.2f} ms, get_image {1e3 * (time.perf_counter() - t2):.2f} ms", file=sys.stderr)
         if world > 1:
             tmp = himg.reshape(-1).cuda(non_blocking=True)
             dist.all_reduce(tmp); torch.cuda.synchronize()
@@ -321,7 +325,7 @@ def main():
             pt = kdpt.default_params(); ctypes.memmove(ctypes.byref(pt), ctypes.byref(params), ctypes.sizeof(pt)); pt.testingmode = 1
             ctx.render(1, S, 1, pt)
             st = ctx.render(1 + S, S, 1, pt)
-            nb = S * min(8, sc.trace_depth)
+            nb = max(1, st["intersect_launches"])
             launch_ms = st["intersect_ms"] / nb
             bytes_per_launch = ab["bytes_per_ray_bounce"] * st["ray_bounces"] / nb
             achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9

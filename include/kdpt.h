@@ -110,6 +110,7 @@ typedef struct {            /* filled by kdpt_render */
     uint64_t launches;      /* kernels launched */
     float intersectMs;      /* device time of the intersect kernels (the reference's TESTINGMODE number) */
     float totalMs;          /* device time of the whole call */
+    uint64_t intersectLaunches; /* number of intersect (bounce) kernel launches behind intersectMs */
 } kdpt_render_stats;
 
 /* the reference's per-path records, for the stage-level entry points below */

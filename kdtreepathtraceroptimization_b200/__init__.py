@@ -67,7 +67,7 @@ class CParams(ctypes.Structure):
 
 class CRenderStats(ctypes.Structure):
     _fields_ = [("rayBounces", ctypes.c_uint64), ("launches", ctypes.c_uint64), ("intersectMs", ctypes.c_float),
-                ("totalMs", ctypes.c_float)]
+                ("totalMs", ctypes.c_float), ("intersectLaunches", ctypes.c_uint64)]
 
 
 def default_params(**kw) -> CParams:
@@ -265,7 +265,8 @@ class Context:
         st = CRenderStats()
         _check(self._lib.kdpt_render(self._h, int(iter_begin), int(iter_count), int(iter_stride), ctypes.byref(p),
                                      ctypes.byref(st)), "kdpt_render")
-        return dict(ray_bounces=st.rayBounces, launches=st.launches, intersect_ms=st.intersectMs, total_ms=st.totalMs)
+        return dict(ray_bounces=st.rayBounces, launches=st.launches, intersect_ms=st.intersectMs, total_ms=st.totalMs,
+                    intersect_launches=st.intersectLaunches)
 
     def generate_rays(self, iteration: int, params: CParams | None = None) -> np.ndarray:
         p = params if params is not None else default_params()

@@ -13,17 +13,46 @@ int cudaFail(cudaError_t e, const char* what)
     return KDPT_ERR_CUDA;
 }
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold lifted, so
+// that pathtraceFree + pathtraceInit — which the reference runs on every camera move (main.cpp:1134-1137) — reuses the
+// previous context's memory instead of paying cudaMalloc/cudaFree for ~1 GB of path state each time.
+static cudaStream_t allocStream()
+{
+    static thread_local cudaStream_t streams[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!streams[dev]) {
+        cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return streams[dev];
+}
+
 int DeviceBuffer::alloc(size_t n)
 {
     release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e != cudaSuccess) { p = nullptr; return cudaFail(e, "cudaMalloc"); }
+    cudaStream_t as = allocStream();
+    cudaError_t e = cudaMallocAsync(&p, n, as);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(as);       // usable from any stream afterwards
+    if (e != cudaSuccess) { p = nullptr; return cudaFail(e, "cudaMallocAsync"); }
     bytes = n;
     return KDPT_OK;
 }
 int DeviceBuffer::ensure(size_t n) { return n <= bytes && p ? KDPT_OK : alloc(n + n / 4); }
-void DeviceBuffer::release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+void DeviceBuffer::release()
+{
+    if (p) {
+        cudaDeviceSynchronize();                                // nothing enqueued anywhere may still touch it (what cudaFree implies)
+        cudaFreeAsync(p, allocStream());
+    }
+    p = nullptr; bytes = 0;
+}
 
 template <class T>
 static int upload(DeviceBuffer& buf, const std::vector<T>& v, const T** devPtr, cudaStream_t s)
@@ -91,7 +120,7 @@ int kdpt_destroy(kdpt_ctx* ctx)
     for (auto& b : ctx->treeMem) b.release();
     DeviceBuffer* bufs[] = {&ctx->scene.geoms, &ctx->scene.materials, &ctx->scene.offsets, &ctx->rays, &ctx->tmin,
                             &ctx->hits, &ctx->counter, &ctx->image, &ctx->pathsA, &ctx->pathsB, &ctx->isects,
-                            &ctx->scanTmp, &ctx->keysTmp, &ctx->hist};
+                            &ctx->scanTmp, &ctx->keysTmp, &ctx->hist, &ctx->accum};
     for (auto* b : bufs) b->release();
     if (ctx->pinnedIn) cudaFreeHost(ctx->pinnedIn);
     if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);

@@ -258,6 +258,118 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
     }
 }
 
+#if defined(__CUDACC__)
+// ---- exact closest hit, warp-cooperative leaves ---------------------------------------------------------------
+// Same traversal as traceExact (so the same leaves and triangles are tested and the same hit is returned), but the
+// reference tree's fat leaves (hundreds of triangles: the builder stops at depth 14) are not walked by one lane while
+// 31 idle: every lane descends its own ray to its next leaf, then the warp takes the pending leaves with at least
+// COOP_MIN triangles one at a time — the owner's ray is broadcast with shuffles, the 32 lanes test 32 consecutive
+// triangles per step (three fully coalesced loads), and the best candidate (min nudged t, ties to the smaller
+// canonical index: the order-independent form of the reference's strict `t_min > t`) goes back to the owner.
+// Small leaves stay lane-private. Must be called by all 32 lanes of a warp (lanes without a ray pass active=false).
+template <int STACK, int COOP_MIN>
+__device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o, V3 d, float tMinIn, float eps, Hit& H)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    initHit(H, tMinIn);
+    bool run = active && T.numNodes != 0;
+    float len = 0.f, slack = 0.f, t0 = 0.f, t1 = 0.f, zbound = FLT_MAX;
+    V3 inv = mk(0, 0, 0);
+    if (run) {
+        len = length(d);
+        if (!(len > 0.0f) || !(len <= FLT_MAX)) run = false;
+    }
+    if (run) {
+        slack = kExitSlack / len;
+        inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        if (!slab(o, inv, T.rootLo, T.rootHi, t0, t1)) run = false;
+        else {
+            if (!(t0 > 0.0f)) t0 = 0.0f;
+            zbound = tMinIn < FLT_MAX ? tMinIn / len : FLT_MAX;
+        }
+    }
+    RayStack<STACK> st; st.clear();
+    unsigned cur = 0; float tmin = t0, tmax = t1;
+    while (__any_sync(FULL, run)) {
+        int start = 0, count = 0;
+        if (run) {
+            uint4 nd = __ldg(T.nodes + cur);
+            while ((nd.w & 3u) != kLeafFlag) {
+                int a = (int)(nd.w & 3u);
+                float split = __int_as_float((int)nd.x);
+                float oa = comp(o, a), da = comp(d, a), ia = comp(inv, a);
+                bool below = oa < split || (oa == split && da <= 0.0f);
+                unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+                float tp = (split - oa) * ia;
+                if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
+                else if (tp <= tmin) cur = farc;
+                else { st.push(farc, tp, tmax); cur = nearc; tmax = tp; }
+                nd = __ldg(T.nodes + cur);
+            }
+            start = (int)nd.x; count = (int)nd.y;
+        }
+        // ---- fat leaves: the whole warp works for one owner at a time ----
+        unsigned big = __ballot_sync(FULL, run && count >= COOP_MIN);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            V3 O = mk(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
+            V3 D = mk(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
+            const int cstart = __shfl_sync(FULL, start, src), ccount = __shfl_sync(FULL, count, src);
+            const float bestT = __shfl_sync(FULL, H.t, src);
+            const int bestTri = __shfl_sync(FULL, H.tri, src);
+            Hit L; L.t = bestT; L.tri = bestTri; L.z = L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
+            for (int k = (int)lane; k < ccount; k += 32) {
+                TriHot tr = loadTri(T, cstart + k);
+                float u, v, z;
+                if (rayTri(O, D, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, true, L);
+            }
+            const bool improved = L.t != bestT || L.tri != bestTri;
+            const unsigned im = __ballot_sync(FULL, improved);
+            if (im) {
+                float kt = improved ? L.t : FLT_MAX; int kc = improved ? L.tri : 0x7fffffff;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    float t2 = __shfl_xor_sync(FULL, kt, off); int c2 = __shfl_xor_sync(FULL, kc, off);
+                    if (t2 < kt || (t2 == kt && c2 < kc)) { kt = t2; kc = c2; }
+                }
+                const int win = __ffs(__ballot_sync(FULL, improved && L.t == kt && L.tri == kc)) - 1;
+                Hit W;
+                W.t = kt; W.tri = kc;
+                W.z = __shfl_sync(FULL, L.z, win); W.u = __shfl_sync(FULL, L.u, win); W.v = __shfl_sync(FULL, L.v, win);
+                W.nx = __shfl_sync(FULL, L.nx, win); W.ny = __shfl_sync(FULL, L.ny, win); W.nz = __shfl_sync(FULL, L.nz, win);
+                W.mtl = __shfl_sync(FULL, L.mtl, win); W.anyMtl = W.mtl;
+                if ((int)lane == src) H = W;
+            }
+        }
+        if (run) {
+            if (count > 0 && count < COOP_MIN) {
+                for (int i = start; i < start + count; i++) {
+                    TriHot tr = loadTri(T, i);
+                    float u, v, z;
+                    if (rayTri(o, d, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
+                }
+            }
+            float zb = H.tri >= 0 ? fminf(H.z, zbound) : zbound;
+            bool found = false;
+            while (st.n > 0) {
+                unsigned n2; float a2, b2;
+                st.pop(n2, a2, b2);
+                if (a2 > zb + slack) continue;
+                cur = n2; tmin = a2; tmax = b2; found = true;
+                break;
+            }
+            if (!found) {
+                if (STACK < kMaxDepth && st.dropped && !(tmax >= t1 || tmax > zb + slack)) {
+                    tmin = tmax; tmax = t1; cur = 0; st.clear();        // kd-restart
+                } else run = false;
+            }
+        }
+    }
+}
+#endif // __CUDACC__
+
 // ---- reference-compatible traversal (KDPT_REF_T1 / KDPT_REF_T2) --------------------------------------------------
 // The reference's parent-pointer state machine visits nodes exactly like this depth-first walk (proved equal on
 // every ray by tests/test_oracle_cpu.py on the CPU restatement, oracle/kdpt_oracle.c:traverse_dfs):

@@ -52,7 +52,7 @@ struct kdpt_ctx {
     void* pinnedIn = nullptr; size_t pinnedInBytes = 0;
     void* pinnedOut = nullptr; size_t pinnedOutBytes = 0;
     // render loop state
-    kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist;
+    kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist, accum;
     int pixelCount = 0;
     float* boundImage = nullptr;        // caller-owned radiance buffer (kdpt_bind_image)
     cudaStream_t ownStream = nullptr;   // `stream` may point at a caller's stream (kdpt_set_stream)

@@ -24,6 +24,10 @@ constexpr int kThreads = 128;
 constexpr int kMaxBounces = 8;          // the reference's hard cap `depth > 7`, pathtrace.cu:2608
 constexpr int kMaxSmemGeoms = 32;
 constexpr int kSortTile = 512;
+#ifndef KDPT_COOP_MIN
+#define KDPT_COOP_MIN 16
+#endif
+constexpr int kBounceCoopMin = KDPT_COOP_MIN;
 
 struct PathSoA {
     float4* od;   // origin.xyz, sdepth
@@ -39,11 +43,38 @@ struct IterConst {
     float qw, qx, qy, qz;      // DOF rotation quaternion
 };
 
+constexpr int kMaxBatch = 16;           // iterations (samples) processed together by every launch
+
 struct LoopState {
-    int np[kMaxBounces + 2];                 // live paths at the start of each bounce
-    unsigned ticket[4 * (kMaxBounces + 1)];  // packet counters: [b] bounce kernel, [9+b] compaction, [18+b]/[27+b] sort
+    int np[kMaxBatch][kMaxBounces + 2];      // live paths of each batched iteration at the start of each bounce
+    unsigned ticket[2 * (kMaxBounces + 1)];  // packet counters: [b] bounce kernel, [9+b] compaction
     unsigned long long bounceRays[kMaxBounces];
 };
+
+// A batch = B consecutive iterations of this rank, each owning one segment of `cap` path slots (and capPackets packet
+// slots). Paths never move between segments: the reference seeds its RNG with the path's index inside its own
+// iteration's compacted array (pathtrace.cu:1691), so compaction and sort are per segment.
+struct Batch {
+    int B, cap, capPackets, iterBase, iterStride, npix;
+};
+struct IterConsts { IterConst c[kMaxBatch]; };
+
+// flat packet ticket -> (segment, first path of the packet); pk[] = exclusive prefix of packets per segment (smem)
+__device__ __forceinline__ void buildPacketPrefix(int* pk, const LoopState* st, int B, int depth)
+{
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int s = 0; s < B; s++) { pk[s] = acc; acc += (st->np[s][depth] + 31) >> 5; }
+        pk[B] = acc;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ int findSegment(const int* pk, int B, int t)
+{
+    int s = 0;
+    while (s + 1 < B && t >= pk[s + 1]) s++;
+    return s;
+}
 
 struct SceneView {
     const kdpt_geom* geoms; int numGeoms;
@@ -105,15 +136,16 @@ static IterConst makeIterConst(int iter, const kdpt_params& p)
 
 // ---- generateRayFromCamera ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-generateRaysKernel(kdpt_camera cam, IterConst ic, int traceDepth, float focal, PathSoA P, LoopState* st)
+generateRaysKernel(kdpt_camera cam, IterConsts ics, Batch bt, int traceDepth, float focal, PathSoA P, LoopState* st,
+                   float* __restrict__ accum)
 {
-    int n = cam.resolution[0] * cam.resolution[1];
-    int index = blockIdx.x * blockDim.x + threadIdx.x;
-    if (index == 0) {
-        st->np[0] = n;
-        for (int k = 0; k < 4 * (kMaxBounces + 1); k++) st->ticket[k] = 0;
-    }
-    if (index >= n) return;
+    const int n = bt.npix;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) for (int k = 0; k < 2 * (kMaxBounces + 1); k++) st->ticket[k] = 0;
+    if (g < bt.B) st->np[g][0] = n;
+    if (g >= bt.B * n) return;
+    const int seg = g / n, index = g - seg * n;
+    const IterConst& ic = ics.c[seg];
     int W = cam.resolution[0], H = cam.resolution[1];
     int x = index % W, y = index / W;
     V3 view = mk(cam.view[0], cam.view[1], cam.view[2]), right = mk(cam.right[0], cam.right[1], cam.right[2]);
@@ -129,107 +161,129 @@ generateRaysKernel(kdpt_camera cam, IterConst ic, int traceDepth, float focal, P
     V3 rot = dir + ((uv * ic.qw) + uuv) * 2.0f;
     V3 org = (pos + dir * focal) - rot * focal;
     dir = normalize(rot);
-    P.od[index] = make_float4(org.x, org.y, org.z, 0.0f);
-    P.dr[index] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-    P.cp[index] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(index));
-    P.bm[index] = make_int2(traceDepth, 0);
+    const size_t slot = (size_t)seg * bt.cap + index;
+    P.od[slot] = make_float4(org.x, org.y, org.z, 0.0f);
+    P.dr[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+    P.cp[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(index));
+    P.bm[slot] = make_int2(traceDepth, 0);
+    if (accum) {        // this iteration's contribution to the pixel; every pixel's path writes it at most once
+        float* a = accum + 3 * ((size_t)seg * n + index);
+        a[0] = 0.f; a[1] = 0.f; a[2] = 0.f;
+    }
 }
 
 // ---- one bounce: intersect (+scatter) + shade + gather, persistent warps pulling 32-path packets ------------------
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
-bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, float* __restrict__ image,
+bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch bt, float* __restrict__ accum,
              int* __restrict__ packetCount, kdpt_intersection* __restrict__ isectOut)
 {
     __shared__ kdpt_geom sGeoms[kMaxSmemGeoms];
+    __shared__ int pk[kMaxBatch + 1];
     const int ng = S.numGeoms < kMaxSmemGeoms ? S.numGeoms : kMaxSmemGeoms;
     {
         const unsigned* src = reinterpret_cast<const unsigned*>(S.geoms);
         unsigned* dst = reinterpret_cast<unsigned*>(sGeoms);
         for (int k = threadIdx.x; k < ng * (int)(sizeof(kdpt_geom) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
     }
-    __syncthreads();
-    const int n = st->np[A.depth];
+    buildPacketPrefix(pk, st, bt.B, A.depth);
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long liveLocal = 0;
     for (;;) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&st->ticket[A.depth], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= (unsigned)n) break;
-        unsigned i = base + lane;
+        int ticket = 0;
+        if (lane == 0) ticket = (int)atomicAdd(&st->ticket[A.depth], 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= pk[bt.B]) break;
+        const int seg = findSegment(pk, bt.B, ticket);
+        const int n = st->np[seg][A.depth];
+        const unsigned i = (unsigned)(ticket - pk[seg]) * 32u + lane;      // path index inside its iteration
+        const size_t slot = (size_t)seg * bt.cap + i;
+        const int iter = bt.iterBase + seg * bt.iterStride;
         bool alive = false, live = false;
+        // ---- phase A (per lane): load the path, test the analytic geoms ----
+        int2 bm = make_int2(0, 0);
+        float4 od = make_float4(0, 0, 0, 0), dr = od, cp = od;
+        PathRay r; r.o = mk(0, 0, 0); r.d = mk(0, 0, 0); r.inside = false; r.sdepth = 0.f;
+        float tMin = FLT_MAX; int hitGeom = -1; V3 ipoint = mk(0, 0, 0), normal = mk(0, 0, 0);
         if (i < (unsigned)n) {
-            int2 bm = P.bm[i];
-            int remaining = bm.x;
-            if (remaining > 0) {
+            bm = P.bm[slot];
+            if (bm.x > 0) {
                 live = true;
-                float4 od = P.od[i], dr = P.dr[i], cp = P.cp[i];
-                PathRay r; r.o = mk(od.x, od.y, od.z); r.d = mk(dr.x, dr.y, dr.z); r.inside = dr.w != 0.0f; r.sdepth = od.w;
-                V3 color = mk(cp.x, cp.y, cp.z);
-                float t = 0.0f; int matId = 0; V3 normal = mk(0, 0, 0);   // dev_intersections is memset to 0 per bounce
-                if (A.stages & KDPT_STAGE_INTERSECT) {
-                    float tMin = FLT_MAX; int hitGeom = -1; V3 ipoint = mk(0, 0, 0);
-                    for (int g = 0; g < S.numGeoms; g++) {
-                        V3 pt, nr;
-                        float tg = g < ng ? geomTest(sGeoms[g], r.o, r.d, pt, nr) : geomTest(S.geoms[g], r.o, r.d, pt, nr);
-                        if (tg > 0.0f && tMin > tg) { tMin = tg; hitGeom = g; ipoint = pt; normal = nr; }
-                    }
-                    Hit H;
-                    if (MODE == KDPT_FULLSTACK) traceExact<kMaxDepth, false>(T, r.o, r.d, tMin, 0.00001f, H, nullptr);
-                    else if (MODE == KDPT_SHORTSTACK) traceExact<4, false>(T, r.o, r.d, tMin, 0.0001f, H, nullptr);
-                    else if (MODE == KDPT_REF_T1) traceRef<false>(T, r.o, r.d, tMin, H, nullptr);
-                    else traceRef<true>(T, r.o, r.d, tMin, H, nullptr);
-                    bool objHit = H.tri >= 0;
-                    if (objHit) {
-                        // the reference's nudged point: o + d*z + n*eps (pathtrace.cu:993-995)
-                        normal = mk(H.nx, H.ny, H.nz);
-                        ipoint = (r.o + r.d * H.z) + normal * A.eps;
-                        tMin = H.t;
-                        // reference: material of the LAST triangle glm accepted (pathtrace.cu:991); exact modes: of the hit
-                        int mtl = (MODE == KDPT_REF_T1 || MODE == KDPT_REF_T2) ? H.anyMtl : H.mtl;
-                        matId = mtl + T.materialSize - 1;
-                    } else if (hitGeom >= 0) matId = S.geoms[hitGeom].materialid;
-                    // multi-shape OBJs index past materials[] in the reference (Appendix A #5); stay in bounds here
-                    matId = matId < 0 ? 0 : (matId >= S.numMaterials ? S.numMaterials - 1 : matId);
-                    if (!objHit && hitGeom < 0) t = -1.0f;          // pathtrace.cu:1683-1686
-                    else {
-                        const kdpt_material m = S.materials[matId];
-                        scatterRay(r, ipoint, normal, m, pathSeed(A.iter, (int)i, A.depth), A.softness);
-                        t = tMin;
-                        bm.y = matId;
-                    }
-                    if (isectOut) {
-                        kdpt_intersection is; is.t = t; is.surfaceNormal[0] = t == -1.0f ? 0.f : normal.x;
-                        is.surfaceNormal[1] = t == -1.0f ? 0.f : normal.y; is.surfaceNormal[2] = t == -1.0f ? 0.f : normal.z;
-                        is.materialId = t == -1.0f ? 0 : matId;
-                        isectOut[i] = is;
-                    }
-                } else if (isectOut) {      // shade-only call: the caller supplies the intersections
-                    kdpt_intersection is = isectOut[i];
-                    t = is.t; matId = is.materialId;
-                }
-                if (A.stages & KDPT_STAGE_SHADE) {
-                    if (t > 0.0f) remaining = shadeHit(S.materials[matId], A.enableSss != 0, r.sdepth, color, remaining);
-                    else { color = mk(0, 0, 0); remaining = 0; }
-                }
-                if ((A.stages & 4) && remaining == 0) {     // partialGather: one live path per pixel, no atomics needed
-                    int pix = __float_as_int(cp.w);
-                    float* px = image + 3 * (size_t)pix;
-                    px[0] += color.x; px[1] += color.y; px[2] += color.z;
-                }
-                P.od[i] = make_float4(r.o.x, r.o.y, r.o.z, r.sdepth);
-                P.dr[i] = make_float4(r.d.x, r.d.y, r.d.z, r.inside ? 1.0f : 0.0f);
-                P.cp[i] = make_float4(color.x, color.y, color.z, cp.w);
-                bm.x = remaining;
-                P.bm[i] = bm;
+                od = P.od[slot]; dr = P.dr[slot]; cp = P.cp[slot];
+                r.o = mk(od.x, od.y, od.z); r.d = mk(dr.x, dr.y, dr.z); r.inside = dr.w != 0.0f; r.sdepth = od.w;
             }
-            alive = remaining > 0;
         }
+        const bool doIsect = live && (A.stages & KDPT_STAGE_INTERSECT);
+        if (doIsect) {
+            for (int g = 0; g < S.numGeoms; g++) {
+                V3 pt, nr;
+                float tg = g < ng ? geomTest(sGeoms[g], r.o, r.d, pt, nr) : geomTest(S.geoms[g], r.o, r.d, pt, nr);
+                if (tg > 0.0f && tMin > tg) { tMin = tg; hitGeom = g; ipoint = pt; normal = nr; }
+            }
+        }
+        // ---- phase B (whole warp): KD traversal + triangle tests ----
+        Hit H;
+        if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, doIsect, r.o, r.d, tMin, 0.00001f, H);
+        else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, doIsect, r.o, r.d, tMin, 0.0001f, H);
+        else if (doIsect) {
+            if (MODE == KDPT_REF_T1) traceRef<false>(T, r.o, r.d, tMin, H, nullptr);
+            else traceRef<true>(T, r.o, r.d, tMin, H, nullptr);
+        }
+        // ---- phase C (per lane): scatter, shade, gather, write back ----
+        if (live) {
+            int remaining = bm.x;
+            V3 color = mk(cp.x, cp.y, cp.z);
+            float t = 0.0f; int matId = 0;      // dev_intersections is memset to 0 per bounce (pathtrace.cu:2473)
+            if (doIsect) {
+                bool objHit = H.tri >= 0;
+                if (objHit) {
+                    // the reference's nudged point: o + d*z + n*eps (pathtrace.cu:993-995)
+                    normal = mk(H.nx, H.ny, H.nz);
+                    ipoint = (r.o + r.d * H.z) + normal * A.eps;
+                    tMin = H.t;
+                    // reference: material of the LAST triangle glm accepted (pathtrace.cu:991); exact modes: of the hit
+                    int mtl = (MODE == KDPT_REF_T1 || MODE == KDPT_REF_T2) ? H.anyMtl : H.mtl;
+                    matId = mtl + T.materialSize - 1;
+                } else if (hitGeom >= 0) matId = S.geoms[hitGeom].materialid;
+                // multi-shape OBJs index past materials[] in the reference (Appendix A #5); stay in bounds here
+                matId = matId < 0 ? 0 : (matId >= S.numMaterials ? S.numMaterials - 1 : matId);
+                if (!objHit && hitGeom < 0) t = -1.0f;          // pathtrace.cu:1683-1686
+                else {
+                    const kdpt_material m = S.materials[matId];
+                    scatterRay(r, ipoint, normal, m, pathSeed(iter, (int)i, A.depth), A.softness);
+                    t = tMin;
+                    bm.y = matId;
+                }
+                if (isectOut) {
+                    kdpt_intersection is; is.t = t; is.surfaceNormal[0] = t == -1.0f ? 0.f : normal.x;
+                    is.surfaceNormal[1] = t == -1.0f ? 0.f : normal.y; is.surfaceNormal[2] = t == -1.0f ? 0.f : normal.z;
+                    is.materialId = t == -1.0f ? 0 : matId;
+                    isectOut[slot] = is;
+                }
+            } else if (isectOut) {      // shade-only call: the caller supplies the intersections
+                kdpt_intersection is = isectOut[slot];
+                t = is.t; matId = is.materialId;
+            }
+            if (A.stages & KDPT_STAGE_SHADE) {
+                if (t > 0.0f) remaining = shadeHit(S.materials[matId], A.enableSss != 0, r.sdepth, color, remaining);
+                else { color = mk(0, 0, 0); remaining = 0; }
+            }
+            if ((A.stages & 4) && remaining == 0) {     // partialGather: each pixel's path finishes exactly once per iteration
+                int pix = __float_as_int(cp.w);
+                float* px = accum + 3 * ((size_t)seg * bt.npix + pix);
+                px[0] = color.x; px[1] = color.y; px[2] = color.z;
+            }
+            P.od[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.sdepth);
+            P.dr[slot] = make_float4(r.d.x, r.d.y, r.d.z, r.inside ? 1.0f : 0.0f);
+            P.cp[slot] = make_float4(color.x, color.y, color.z, cp.w);
+            bm.x = remaining;
+            P.bm[slot] = bm;
+            alive = remaining > 0;
+        } else if (i < (unsigned)n) alive = bm.x > 0;
         unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
         unsigned liveMask = __ballot_sync(0xffffffffu, live);
         if (lane == 0) {
-            if (packetCount) packetCount[base >> 5] = __popc(aliveMask);
+            if (packetCount) packetCount[seg * bt.capPackets + (ticket - pk[seg])] = __popc(aliveMask);
             liveLocal += (unsigned)__popc(liveMask);
         }
     }
@@ -240,12 +294,14 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, float*
 // packetCount[k] = survivors in paths [32k, 32k+32). One block turns them into exclusive offsets and publishes the
 // next bounce's path count.
 __global__ void __launch_bounds__(1024)
-scanPacketsKernel(int* __restrict__ packetCount, LoopState* st, int depth, int compaction)
+scanPacketsKernel(int* __restrict__ packetCountAll, LoopState* st, int depth, int compaction, int capPackets)
 {
     __shared__ int warpSums[32];
     __shared__ int carry;
-    const int n = st->np[depth];
-    if (!compaction) { if (threadIdx.x == 0) st->np[depth + 1] = n; return; }
+    const int seg = blockIdx.x;                     // one block per batched iteration
+    int* packetCount = packetCountAll + (size_t)seg * capPackets;
+    const int n = st->np[seg][depth];
+    if (!compaction) { if (threadIdx.x == 0) st->np[seg][depth + 1] = n; return; }
     const int numPackets = (n + 31) >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
@@ -270,27 +326,32 @@ scanPacketsKernel(int* __restrict__ packetCount, LoopState* st, int depth, int c
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) st->np[depth + 1] = carry;
+    if (threadIdx.x == 0) st->np[seg][depth + 1] = carry;
 }
 
 __global__ void __launch_bounds__(kThreads)
-compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset, LoopState* st, int depth)
+compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset, LoopState* st, int depth, Batch bt)
 {
-    const int n = st->np[depth];
+    __shared__ int pk[kMaxBatch + 1];
+    buildPacketPrefix(pk, st, bt.B, depth);
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&st->ticket[9 + depth], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= (unsigned)n) break;
-        unsigned i = base + lane;
+        int ticket = 0;
+        if (lane == 0) ticket = (int)atomicAdd(&st->ticket[9 + depth], 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= pk[bt.B]) break;
+        const int seg = findSegment(pk, bt.B, ticket);
+        const int n = st->np[seg][depth];
+        const int packet = ticket - pk[seg];
+        const unsigned i = (unsigned)packet * 32u + lane;
+        const size_t slot = (size_t)seg * bt.cap + i;
         int2 bm = make_int2(0, 0);
-        if (i < (unsigned)n) bm = P.bm[i];
+        if (i < (unsigned)n) bm = P.bm[slot];
         bool alive = i < (unsigned)n && bm.x != 0;          // is_zero_bounce, pathtrace.cu:103-110
         unsigned mask = __ballot_sync(0xffffffffu, alive);
         if (alive) {
-            int dst = packetOffset[base >> 5] + __popc(mask & ((1u << lane) - 1u));
-            Q.od[dst] = P.od[i]; Q.dr[dst] = P.dr[i]; Q.cp[dst] = P.cp[i]; Q.bm[dst] = bm;
+            size_t dst = (size_t)seg * bt.cap + packetOffset[seg * bt.capPackets + packet] + __popc(mask & ((1u << lane) - 1u));
+            Q.od[dst] = P.od[slot]; Q.dr[dst] = P.dr[slot]; Q.cp[dst] = P.cp[slot]; Q.bm[dst] = bm;
         }
     }
 }
@@ -302,7 +363,7 @@ __global__ void __launch_bounds__(kSortTile)
 sortHistKernel(PathSoA P, LoopState* st, int depth, int shift, unsigned* __restrict__ hist, int maxTiles)
 {
     __shared__ unsigned h[256];
-    const int n = st->np[depth];
+    const int n = st->np[0][depth];                // the sort runs on single-iteration batches only
     const int numTiles = (n + kSortTile - 1) / kSortTile;
     for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
         if (threadIdx.x < 256) h[threadIdx.x] = 0;
@@ -320,7 +381,7 @@ sortScanKernel(LoopState* st, int depth, unsigned* __restrict__ hist, int maxTil
 {
     __shared__ unsigned warpSums[32];
     __shared__ unsigned carry;
-    const int n = st->np[depth];
+    const int n = st->np[0][depth];                // the sort runs on single-iteration batches only
     const int numTiles = (n + kSortTile - 1) / kSortTile;
     const int total = 256 * numTiles;
     if (threadIdx.x == 0) carry = 0;
@@ -352,7 +413,7 @@ __global__ void __launch_bounds__(kSortTile)
 sortScatterKernel(PathSoA P, PathSoA Q, LoopState* st, int depth, int shift, const unsigned* __restrict__ hist, int maxTiles)
 {
     __shared__ unsigned short warpDigitCount[kSortTile / 32][256];
-    const int n = st->np[depth];
+    const int n = st->np[0][depth];                // the sort runs on single-iteration batches only
     const int numTiles = (n + kSortTile - 1) / kSortTile;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
@@ -376,13 +437,26 @@ sortScatterKernel(PathSoA P, PathSoA Q, LoopState* st, int depth, int shift, con
 }
 
 // finalGather (compaction off), pathtrace.cu:2373-2383: every path adds its colour
-__global__ void finalGatherKernel(PathSoA P, LoopState* st, int depth, float* __restrict__ image)
+__global__ void finalGatherKernel(PathSoA P, LoopState* st, int depth, Batch bt, float* __restrict__ accum)
 {
-    const int n = st->np[depth];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 cp = P.cp[i];
-        float* px = image + 3 * (size_t)__float_as_int(cp.w);
-        px[0] += cp.x; px[1] += cp.y; px[2] += cp.z;
+    for (int seg = 0; seg < bt.B; seg++) {
+        const int n = st->np[seg][depth];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            float4 cp = P.cp[(size_t)seg * bt.cap + i];
+            float* px = accum + 3 * ((size_t)seg * bt.npix + __float_as_int(cp.w));
+            px[0] = cp.x; px[1] = cp.y; px[2] = cp.z;
+        }
+    }
+}
+
+// image += contribution of iteration 0, then 1, ... of the batch: the same summation order as rendering the
+// iterations one after the other, so the result does not depend on the batch size
+__global__ void accumulateKernel(float* __restrict__ image, const float* __restrict__ accum, int B, int numFloats)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < numFloats; k += gridDim.x * blockDim.x) {
+        float v = image[k];
+        for (int s = 0; s < B; s++) v += accum[(size_t)s * numFloats + k];
+        image[k] = v;
     }
 }
 
@@ -390,7 +464,7 @@ __global__ void finalGatherKernel(PathSoA P, LoopState* st, int depth, float* __
 __global__ void packPathsKernel(const kdpt_path_segment* __restrict__ in, int n, PathSoA P, LoopState* st, int depth)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { st->np[depth] = n; st->ticket[depth] = 0; }
+    if (i == 0) { st->np[0][depth] = n; st->ticket[depth] = 0; }
     if (i >= n) return;
     kdpt_path_segment s = in[i];
     P.od[i] = make_float4(s.origin[0], s.origin[1], s.origin[2], s.sdepth);
@@ -418,13 +492,17 @@ struct RenderBuffers {
     int* packetCount;
     unsigned* hist; int maxTiles;
     float* image;
+    float* accum;
+    int cap, capPackets;
 };
 
-static int ensureRenderBuffers(kdpt_ctx* ctx, int n, RenderBuffers& rb)
+// n = path slots per iteration, batch = iterations per launch
+static int ensureRenderBuffers(kdpt_ctx* ctx, int n, int batch, RenderBuffers& rb, bool needAccum)
 {
     int rc;
-    size_t per = sizeof(float4) * 3 + sizeof(int2);
-    if ((rc = ctx->pathsA.ensure(per * (size_t)n)) || (rc = ctx->pathsB.ensure(per * (size_t)n))) return rc;
+    const size_t per = sizeof(float4) * 3 + sizeof(int2);
+    const size_t slots = (size_t)n * batch;
+    if ((rc = ctx->pathsA.ensure(per * slots)) || (rc = ctx->pathsB.ensure(per * slots))) return rc;
     auto carve = [&](DeviceBuffer& b, PathSoA& P) {
         char* p = (char*)b.p;
         size_t cap = b.bytes / per;
@@ -436,12 +514,18 @@ static int ensureRenderBuffers(kdpt_ctx* ctx, int n, RenderBuffers& rb)
     if ((rc = ctx->scanTmp.ensure(sizeof(LoopState)))) return rc;
     if (fresh) KDPT_CUDA(cudaMemsetAsync(ctx->scanTmp.p, 0, sizeof(LoopState), ctx->stream));
     rb.st = ctx->scanTmp.as<LoopState>();
-    if ((rc = ctx->keysTmp.ensure(sizeof(int) * (size_t)((n + 31) / 32 + 1)))) return rc;
+    rb.cap = n; rb.capPackets = (n + 31) / 32 + 1;
+    if ((rc = ctx->keysTmp.ensure(sizeof(int) * (size_t)rb.capPackets * batch))) return rc;
     rb.packetCount = ctx->keysTmp.as<int>();
     rb.maxTiles = (n + kSortTile - 1) / kSortTile + 1;
     if ((rc = ctx->hist.ensure(sizeof(unsigned) * 256 * (size_t)rb.maxTiles))) return rc;
     rb.hist = ctx->hist.as<unsigned>();
     rb.image = ctx->boundImage ? ctx->boundImage : ctx->image.as<float>();
+    rb.accum = nullptr;
+    if (needAccum) {
+        if ((rc = ctx->accum.ensure(sizeof(float) * 3 * (size_t)ctx->pixelCount * batch))) return rc;
+        rb.accum = ctx->accum.as<float>();
+    }
     return KDPT_OK;
 }
 
@@ -465,20 +549,20 @@ static int checkParams(const kdpt_params* p)
     return KDPT_OK;
 }
 
-static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers& rb, PathSoA P, int iter, int depth,
+static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers& rb, PathSoA P, const Batch& bt, int depth,
                         int stages, kdpt_intersection* dIsects, uint64_t& launches)
 {
     SceneView S{ctx->scene.geoms.as<kdpt_geom>(), ctx->scene.numGeoms, ctx->scene.materials.as<kdpt_material>(), ctx->scene.numMaterials};
-    BounceArgs A; A.iter = iter; A.depth = depth; A.stages = stages; A.softness = p.softness; A.enableSss = p.enableSss;
+    BounceArgs A; A.iter = bt.iterBase; A.depth = depth; A.stages = stages; A.softness = p.softness; A.enableSss = p.enableSss;
     A.eps = (p.mode == KDPT_SHORTSTACK || p.mode == KDPT_REF_T2) ? 0.0001f : 0.00001f;
     int grid = ctx->numSMs * 8;
     cudaStream_t s = ctx->stream;
     int* pc = p.compaction ? rb.packetCount : nullptr;
     switch (p.mode) {
-    case KDPT_FULLSTACK: bounceKernel<KDPT_FULLSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
-    case KDPT_SHORTSTACK: bounceKernel<KDPT_SHORTSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
-    case KDPT_REF_T1: bounceKernel<KDPT_REF_T1><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
-    default: bounceKernel<KDPT_REF_T2><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, rb.image, pc, dIsects); break;
+    case KDPT_FULLSTACK: bounceKernel<KDPT_FULLSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
+    case KDPT_SHORTSTACK: bounceKernel<KDPT_SHORTSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
+    case KDPT_REF_T1: bounceKernel<KDPT_REF_T1><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
+    default: bounceKernel<KDPT_REF_T2><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
     }
     launches++;
     KDPT_CUDA(cudaGetLastError());
@@ -561,8 +645,13 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     if ((rc = ensureImage(ctx))) return rc;
     const kdpt_params& p = *params;
     const int n = ctx->pixelCount;
+    // iterations per launch: bounded by kMaxBatch and by ~1.5 GB of path state; the material sort is per iteration
+    int maxBatch = kMaxBatch;
+    while (maxBatch > 1 && (size_t)maxBatch * n * 128 > ((size_t)3 << 29)) maxBatch >>= 1;
+    if (p.sortByMaterial == 2) maxBatch = 1;
+    if (iter_count < maxBatch) maxBatch = iter_count > 0 ? iter_count : 1;
     RenderBuffers rb;
-    if ((rc = ensureRenderBuffers(ctx, n, rb))) return rc;
+    if ((rc = ensureRenderBuffers(ctx, n, maxBatch, rb, true))) return rc;
     cudaStream_t s = ctx->stream;
     uint64_t launches = 0;
     unsigned long long before[kMaxBounces], after[kMaxBounces];
@@ -578,26 +667,31 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     const int grid = ctx->numSMs * 8;
     int sortPasses = 1;
     for (int m = ctx->scene.numMaterials + 1; m > 256; m >>= 8) sortPasses++;
-    for (int k = 0; k < iter_count; k++) {
-        const int iter = iter_begin + k * iter_stride;
-        IterConst ic = makeIterConst(iter, p);
-        generateRaysKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ic, ctx->scene.traceDepth, p.focalLength, rb.A, rb.st);
+    // remainingBounces starts at traceDepth and drops every bounce, so nothing survives min(8, traceDepth) bounces
+    const int maxBounces = ctx->scene.traceDepth < kMaxBounces ? (ctx->scene.traceDepth < 0 ? 0 : ctx->scene.traceDepth) : kMaxBounces;
+    for (int k = 0; k < iter_count;) {
+        // the reference sorts only in iteration 2 (pathtrace.cu:2600): that iteration gets a batch of its own
+        auto sorts = [&](int kk) { int it = iter_begin + kk * iter_stride; return p.sortByMaterial == 2 || (p.sortByMaterial == 1 && it == 2); };
+        int B = 1;
+        const bool sortThis = sorts(k);
+        if (!sortThis) while (B < maxBatch && k + B < iter_count && !sorts(k + B)) B++;
+        Batch bt; bt.B = B; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = iter_begin + k * iter_stride;
+        bt.iterStride = iter_stride; bt.npix = n;
+        IterConsts ics;
+        for (int q = 0; q < B; q++) ics.c[q] = makeIterConst(bt.iterBase + q * iter_stride, p);
+        generateRaysKernel<<<(B * n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ics, bt, ctx->scene.traceDepth, p.focalLength, rb.A, rb.st, rb.accum);
         launches++;
         PathSoA cur = rb.A, other = rb.B;
-        const bool sortThis = p.sortByMaterial == 2 || (p.sortByMaterial == 1 && iter == 2);
-        int depth = 0;
-        // remainingBounces starts at traceDepth and drops every bounce, so nothing survives min(8, traceDepth) bounces
-        const int maxBounces = ctx->scene.traceDepth < kMaxBounces ? (ctx->scene.traceDepth < 0 ? 0 : ctx->scene.traceDepth) : kMaxBounces;
-        for (; depth < maxBounces; depth++) {
+        for (int depth = 0; depth < maxBounces; depth++) {
             int stages = KDPT_STAGE_INTERSECT | KDPT_STAGE_SHADE | (p.compaction ? 4 : 0);
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (timing) { if ((rc = nextEvent(t0)) || (rc = nextEvent(t1))) return rc; KDPT_CUDA(cudaEventRecord(t0, s)); }
-            if ((rc = launchBounce(ctx, p, rb, cur, iter, depth, stages, nullptr, launches))) return rc;
+            if ((rc = launchBounce(ctx, p, rb, cur, bt, depth, stages, nullptr, launches))) return rc;
             if (timing) KDPT_CUDA(cudaEventRecord(t1, s));
-            scanPacketsKernel<<<1, 1024, 0, s>>>(rb.packetCount, rb.st, depth, p.compaction);
+            scanPacketsKernel<<<B, 1024, 0, s>>>(rb.packetCount, rb.st, depth, p.compaction, rb.capPackets);
             launches++;
             if (p.compaction) {
-                compactScatterKernel<<<grid, kThreads, 0, s>>>(cur, other, rb.packetCount, rb.st, depth);
+                compactScatterKernel<<<grid, kThreads, 0, s>>>(cur, other, rb.packetCount, rb.st, depth, bt);
                 launches++;
                 PathSoA t = cur; cur = other; other = t;
             }
@@ -612,10 +706,13 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
             }
         }
         if (!p.compaction) {
-            finalGatherKernel<<<grid, 256, 0, s>>>(cur, rb.st, maxBounces, rb.image);
+            finalGatherKernel<<<grid, 256, 0, s>>>(cur, rb.st, maxBounces, bt, rb.accum);
             launches++;
         }
+        accumulateKernel<<<grid, 256, 0, s>>>(rb.image, rb.accum, B, 3 * n);
+        launches++;
         KDPT_CUDA(cudaGetLastError());
+        k += B;
     }
     ctx->launches += launches;
     if (stats) {
@@ -631,6 +728,7 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
             float ms = 0.f;
             KDPT_CUDA(cudaEventElapsedTime(&ms, ctx->eventPool[k], ctx->eventPool[k + 1]));
             stats->intersectMs += ms;
+            stats->intersectLaunches++;
         }
     }
     return KDPT_OK;
@@ -645,11 +743,12 @@ int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_
     if ((rc = ensureImage(ctx))) return rc;
     const int n = ctx->pixelCount;
     RenderBuffers rb;
-    if ((rc = ensureRenderBuffers(ctx, n, rb))) return rc;
+    if ((rc = ensureRenderBuffers(ctx, n, 1, rb, false))) return rc;
     if ((rc = ctx->isects.ensure(sizeof(kdpt_path_segment) * (size_t)n))) return rc;
     cudaStream_t s = ctx->stream;
-    IterConst ic = makeIterConst(iter, *params);
-    generateRaysKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ic, ctx->scene.traceDepth, params->focalLength, rb.A, rb.st);
+    IterConsts ics; ics.c[0] = makeIterConst(iter, *params);
+    Batch bt; bt.B = 1; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = iter; bt.iterStride = 1; bt.npix = n;
+    generateRaysKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ics, bt, ctx->scene.traceDepth, params->focalLength, rb.A, rb.st, nullptr);
     unpackPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(rb.A, n, ctx->isects.as<kdpt_path_segment>());
     KDPT_CUDA(cudaGetLastError());
     KDPT_CUDA(cudaMemcpyAsync(out, ctx->isects.p, sizeof(kdpt_path_segment) * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -670,7 +769,8 @@ int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, k
     if (n == 0) return KDPT_OK;
     KDPT_CUDA(cudaSetDevice(ctx->device));
     RenderBuffers rb;
-    if ((rc = ensureRenderBuffers(ctx, n, rb))) return rc;
+    if ((rc = ensureRenderBuffers(ctx, n, 1, rb, false))) return rc;
+    Batch bt; bt.B = 1; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = iter; bt.iterStride = 1; bt.npix = n;
     size_t pb = sizeof(kdpt_path_segment) * (size_t)n, ib = sizeof(kdpt_intersection) * (size_t)n;
     if ((rc = ctx->isects.ensure(pb + ib))) return rc;
     kdpt_path_segment* dPaths = ctx->isects.as<kdpt_path_segment>();
@@ -682,7 +782,7 @@ int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, k
     packPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(dPaths, n, rb.A, rb.st, depth);
     kdpt_params p = *params; p.compaction = 0;
     uint64_t launches = 0;
-    if ((rc = launchBounce(ctx, p, rb, rb.A, iter, depth, stages, dIs, launches))) return rc;
+    if ((rc = launchBounce(ctx, p, rb, rb.A, bt, depth, stages, dIs, launches))) return rc;
     unpackPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(rb.A, n, dPaths);
     KDPT_CUDA(cudaGetLastError());
     KDPT_CUDA(cudaMemcpyAsync(paths, dPaths, pb, cudaMemcpyDeviceToHost, s));

@@ -32,10 +32,14 @@ KDPT_HD unsigned pathSeed(int iter, int index, int depth)
 // uniform_real_distribution<float>(0,1): float(x - 1) / (1.0f + float(2147483645))
 struct Rng {
     unsigned x;
-    KDPT_HD void seed(unsigned s) { unsigned v = s % 2147483647u; x = v == 0 ? 1u : v; }
+    // modulo 2^31-1 without a 64-bit division: 2^31 == 1 (mod m), so fold the high bits onto the low ones (exact)
+    KDPT_HD void seed(unsigned s) { unsigned v = (s & 0x7fffffffu) + (s >> 31); if (v >= 2147483647u) v -= 2147483647u; x = v == 0 ? 1u : v; }
     KDPT_HD float u01()
     {
-        x = (unsigned)(((unsigned long long)x * 48271ull) % 2147483647ull);
+        unsigned long long p = (unsigned long long)x * 48271ull;
+        unsigned v = (unsigned)(p & 0x7fffffffull) + (unsigned)(p >> 31);
+        if (v >= 2147483647u) v -= 2147483647u;
+        x = v;
         float r = (float)(x - 1u);
         r /= (1.0f + (float)(2147483646u - 1u));
         return (r * (1.0f - 0.0f)) + 0.0f;

@@ -7,6 +7,10 @@
 namespace kdpt {
 
 constexpr int kTraceThreads = 128;
+#ifndef KDPT_COOP_MIN
+#define KDPT_COOP_MIN 16
+#endif
+constexpr int kCoopMin = KDPT_COOP_MIN;   // leaves with at least this many triangles are tested by the whole warp
 
 // Persistent threads: a fixed grid (a multiple of the SM count) whose warps pull 32-ray packets from a global
 // counter until the batch is drained, so a warp stuck in a fat leaf does not hold back the rest of its block's
@@ -23,16 +27,22 @@ traceKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= (unsigned)n) break;
         unsigned i = base + lane;
-        if (i < (unsigned)n) {
+        const bool active = i < (unsigned)n;
+        V3 o = mk(0, 0, 0), d = mk(0, 0, 0); float tin = FLT_MAX;
+        if (active) {
             const float* r = reinterpret_cast<const float*>(rays + i);
-            V3 o = mk(__ldg(r + 0), __ldg(r + 1), __ldg(r + 2));
-            V3 d = mk(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
-            float tin = tMinIn ? __ldg(tMinIn + i) : FLT_MAX;
-            Hit H;
-            if (MODE == KDPT_FULLSTACK) traceExact<kMaxDepth, false>(T, o, d, tin, 0.00001f, H, nullptr);
-            else if (MODE == KDPT_SHORTSTACK) traceExact<4, false>(T, o, d, tin, 0.0001f, H, nullptr);
-            else if (MODE == KDPT_REF_T1) traceRef<false>(T, o, d, tin, H, nullptr);
+            o = mk(__ldg(r + 0), __ldg(r + 1), __ldg(r + 2));
+            d = mk(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
+            tin = tMinIn ? __ldg(tMinIn + i) : FLT_MAX;
+        }
+        Hit H;
+        if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kCoopMin>(T, active, o, d, tin, 0.00001f, H);
+        else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kCoopMin>(T, active, o, d, tin, 0.0001f, H);
+        else if (active) {
+            if (MODE == KDPT_REF_T1) traceRef<false>(T, o, d, tin, H, nullptr);
             else traceRef<true>(T, o, d, tin, H, nullptr);
+        }
+        if (active) {
             float4* out = reinterpret_cast<float4*>(hits + i);
             out[0] = make_float4(H.t, H.z, H.u, H.v);
             out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
