@@ -15,7 +15,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkdpt.so")
+LIB_PATH = os.environ.get("KDPT_LIB") or os.path.join(_HERE, "libkdpt.so")   # KDPT_LIB: tuning builds only
 
 # ---- reference POD layouts (sizes asserted against the library's static_asserts via kdpt_abi_version) -----------
 NODE = np.dtype([('axis', 'i4'), ('splitPos', 'f4'), ('mins', 'f4', 3), ('maxs', 'f4', 3), ('ID', 'i4'), ('parentID', 'i4'),

@@ -62,6 +62,7 @@ struct Tree {
     float rootLo[3], rootHi[3];
     int tagCand[4];     // nodes[0].leftID, nodes[0].rightID, nodes[1].leftID, nodes[1].rightID (T2 quirk)
     int materialSize;   // hst_scene->materials.size()
+    int laneCost32;     // cost of one lane-private triangle step relative to a cooperative one, x32 (see traceExactWarp)
 };
 
 struct Hit {
@@ -263,7 +264,7 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
 // Same traversal as traceExact (so the same leaves and triangles are tested and the same hit is returned), but the
 // reference tree's fat leaves (hundreds of triangles: the builder stops at depth 14) are not walked by one lane while
 // 31 idle: every lane descends its own ray to its next leaf, then the warp takes the pending leaves with at least
-// COOP_MIN triangles one at a time — the owner's ray is broadcast with shuffles, the 32 lanes test 32 consecutive
+// COOP_MIN triangles (when the cost model below says so) one at a time — the owner's ray is broadcast with shuffles, the 32 lanes test 32 consecutive
 // triangles per step (three fully coalesced loads), and the best candidate (min nudged t, ties to the smaller
 // canonical index: the order-independent form of the reference's strict `t_min > t`) goes back to the owner.
 // Small leaves stay lane-private. Must be called by all 32 lanes of a warp (lanes without a ray pass active=false).
@@ -310,41 +311,57 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
             start = (int)nd.x; count = (int)nd.y;
         }
         // ---- fat leaves: the whole warp works for one owner at a time ----
-        unsigned big = __ballot_sync(FULL, run && count >= COOP_MIN);
-        while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            V3 O = mk(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
-            V3 D = mk(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
-            const int cstart = __shfl_sync(FULL, start, src), ccount = __shfl_sync(FULL, count, src);
-            const float bestT = __shfl_sync(FULL, H.t, src);
-            const int bestTri = __shfl_sync(FULL, H.tri, src);
-            Hit L; L.t = bestT; L.tri = bestTri; L.z = L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
-            for (int k = (int)lane; k < ccount; k += 32) {
-                TriHot tr = loadTri(T, cstart + k);
-                float u, v, z;
-                if (rayTri(O, D, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, true, L);
-            }
-            const bool improved = L.t != bestT || L.tri != bestTri;
-            const unsigned im = __ballot_sync(FULL, improved);
-            if (im) {
-                float kt = improved ? L.t : FLT_MAX; int kc = improved ? L.tri : 0x7fffffff;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    float t2 = __shfl_xor_sync(FULL, kt, off); int c2 = __shfl_xor_sync(FULL, kc, off);
-                    if (t2 < kt || (t2 == kt && c2 < kc)) { kt = t2; kc = c2; }
+        // Which pending leaves are worth it is decided per round with a small cost model: testing a leaf of c triangles
+        // cooperatively costs about 1.5 + c/32 steps (broadcast + reduction + ceil(c/32) tests), while the lane-private
+        // pass that follows costs max(c) over the lanes left to it. Taking the group of near-largest leaves (within
+        // 3/4 of the largest, g lanes) out of the private pass pays when g * (1.5 + m1/32) < a * (m1 - m2), m2 being the
+        // largest leaf that would remain and a = laneCost32/32 the relative cost of a lane-private step (its loads are
+        // scattered over 32 leaves; ~1 when the triangles sit in L1, larger when every lane pulls its own lines from L2). A warp whose lanes all sit in similar leaves therefore stays lane-private,
+        // a warp with one 986-triangle leaf among 20-triangle ones handles just that one together.
+        bool pendingLeaf = run && count > 0;
+        for (;;) {
+            const int m1 = __reduce_max_sync(FULL, pendingLeaf ? count : 0);
+            if (m1 < COOP_MIN) break;
+            const bool inGroup = pendingLeaf && count * 4 >= m1 * 3;
+            unsigned big = __ballot_sync(FULL, inGroup);
+            const int m2 = __reduce_max_sync(FULL, (pendingLeaf && !inGroup) ? count : 0);
+            if (__popc(big) * (48 + m1) >= T.laneCost32 * (m1 - m2)) break;
+            if (inGroup) pendingLeaf = false;
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                V3 O = mk(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
+                V3 D = mk(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
+                const int cstart = __shfl_sync(FULL, start, src), ccount = __shfl_sync(FULL, count, src);
+                const float bestT = __shfl_sync(FULL, H.t, src);
+                const int bestTri = __shfl_sync(FULL, H.tri, src);
+                Hit L; L.t = bestT; L.tri = bestTri; L.z = L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
+                for (int k = (int)lane; k < ccount; k += 32) {
+                    TriHot tr = loadTri(T, cstart + k);
+                    float u, v, z;
+                    if (rayTri(O, D, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, true, L);
                 }
-                const int win = __ffs(__ballot_sync(FULL, improved && L.t == kt && L.tri == kc)) - 1;
-                Hit W;
-                W.t = kt; W.tri = kc;
-                W.z = __shfl_sync(FULL, L.z, win); W.u = __shfl_sync(FULL, L.u, win); W.v = __shfl_sync(FULL, L.v, win);
-                W.nx = __shfl_sync(FULL, L.nx, win); W.ny = __shfl_sync(FULL, L.ny, win); W.nz = __shfl_sync(FULL, L.nz, win);
-                W.mtl = __shfl_sync(FULL, L.mtl, win); W.anyMtl = W.mtl;
-                if ((int)lane == src) H = W;
+                const bool improved = L.t != bestT || L.tri != bestTri;
+                const unsigned im = __ballot_sync(FULL, improved);
+                if (im) {
+                    float kt = improved ? L.t : FLT_MAX; int kc = improved ? L.tri : 0x7fffffff;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        float t2 = __shfl_xor_sync(FULL, kt, off); int c2 = __shfl_xor_sync(FULL, kc, off);
+                        if (t2 < kt || (t2 == kt && c2 < kc)) { kt = t2; kc = c2; }
+                    }
+                    const int win = __ffs(__ballot_sync(FULL, improved && L.t == kt && L.tri == kc)) - 1;
+                    Hit W;
+                    W.t = kt; W.tri = kc;
+                    W.z = __shfl_sync(FULL, L.z, win); W.u = __shfl_sync(FULL, L.u, win); W.v = __shfl_sync(FULL, L.v, win);
+                    W.nx = __shfl_sync(FULL, L.nx, win); W.ny = __shfl_sync(FULL, L.ny, win); W.nz = __shfl_sync(FULL, L.nz, win);
+                    W.mtl = __shfl_sync(FULL, L.mtl, win); W.anyMtl = W.mtl;
+                    if ((int)lane == src) H = W;
+                }
             }
         }
         if (run) {
-            if (count > 0 && count < COOP_MIN) {
+            if (pendingLeaf) {
                 for (int i = start; i < start + count; i++) {
                     TriHot tr = loadTri(T, i);
                     float u, v, z;

@@ -25,7 +25,7 @@ constexpr int kMaxBounces = 8;          // the reference's hard cap `depth > 7`,
 constexpr int kMaxSmemGeoms = 32;
 constexpr int kSortTile = 512;
 #ifndef KDPT_COOP_MIN
-#define KDPT_COOP_MIN 16
+#define KDPT_COOP_MIN 8
 #endif
 constexpr int kBounceCoopMin = KDPT_COOP_MIN;
 
@@ -173,8 +173,11 @@ generateRaysKernel(kdpt_camera cam, IterConsts ics, Batch bt, int traceDepth, fl
 }
 
 // ---- one bounce: intersect (+scatter) + shade + gather, persistent warps pulling 32-path packets ------------------
+#ifndef KDPT_BOUNCE_MIN_BLOCKS
+#define KDPT_BOUNCE_MIN_BLOCKS 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, KDPT_BOUNCE_MIN_BLOCKS)
 bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch bt, float* __restrict__ accum,
              int* __restrict__ packetCount, kdpt_intersection* __restrict__ isectOut)
 {

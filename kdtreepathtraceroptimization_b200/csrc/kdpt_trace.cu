@@ -8,7 +8,7 @@ namespace kdpt {
 
 constexpr int kTraceThreads = 128;
 #ifndef KDPT_COOP_MIN
-#define KDPT_COOP_MIN 16
+#define KDPT_COOP_MIN 8
 #endif
 constexpr int kCoopMin = KDPT_COOP_MIN;   // leaves with at least this many triangles are tested by the whole warp
 

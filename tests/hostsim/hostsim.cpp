@@ -22,7 +22,7 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
     T.numNodes = F.numNodes; T.numTris = F.numTris;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = F.rootLo[a]; T.rootHi[a] = F.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = F.tagCand[k];
-    T.materialSize = materialSize;
+    T.materialSize = materialSize; T.laneCost32 = 32;
     TraceCounters tc = {0, 0, 0};
     unsigned long long cn = 0, cl = 0, ct = 0;
     for (int i = 0; i < n; i++) {
