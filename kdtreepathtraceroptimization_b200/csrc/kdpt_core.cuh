@@ -109,6 +109,37 @@ KDPT_HD int rayTri(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float& u, float& v, float& z
     return z >= 0.0f ? 2 : 1;
 }
 
+// The same predicate for the kernels' hot loops: returns exactly what rayTri returns as far as hit / no hit goes, but
+// skips the IEEE division for triangles that certainly fail a barycentric test. With f = fl(1/a) > 0:
+//   su < -a*2^-120            =>  fl(f*su) < 0 (the product cannot underflow to -0)         => u < 0, reject
+//   su >  a*(1 + 2^-20)       =>  fl(f*su) > 1 (three roundings of 2^-24 each cannot undo it) => u > 1, reject
+// and likewise for v and for u + v (margin 2^-18). Everything that survives the filter is evaluated with the exact
+// sequence above, so accepted hits and their u, v, z are bit-identical. (Only the exact-hit kernels use it: the
+// reference-compatible ones also need the u/v/z glm leaves behind on rejected triangles.)
+KDPT_HD bool rayTriHit(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float& u, float& v, float& z)
+{
+    V3 p = cross(d, e2);
+    float a = dot(e1, p);
+    if (a < FLT_EPSILON) return false;
+    V3 s = o - v0;
+    float su = dot(s, p);
+    const float tiny = a * 7.52316385e-37f;            // a * 2^-120 (exact scaling, a >= 2^-23 so never zero)
+    const float aHi = a * 1.00000095367431640625f;    // a * (1 + 2^-20)
+    if (su < -tiny || su > aHi) return false;
+    V3 q = cross(s, e1);
+    float dq = dot(d, q);
+    if (dq < -tiny || dq > aHi || su + dq > a * 1.000003814697265625f) return false;   // 1 + 2^-18
+    float f = 1.0f / a;
+    u = f * su;
+    if (u < 0.0f) return false;
+    if (u > 1.0f) return false;
+    v = f * dq;
+    if (v < 0.0f) return false;
+    if (v + u > 1.0f) return false;
+    z = f * dot(e2, q);
+    return z >= 0.0f;
+}
+
 // intersectAABBarrays
 KDPT_HD bool slab(V3 o, V3 inv, const float* lo, const float* hi, float& dmin, float& dmax)
 {
@@ -236,7 +267,7 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
             for (int i = start; i < start + count; i++) {
                 TriHot tr = loadTri(T, i);
                 float u, v, z;
-                if (rayTri(o, d, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
+                if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
             }
         }
         float zb = H.tri >= 0 ? fminf(H.z, zbound) : zbound;
@@ -336,10 +367,18 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                 const float bestT = __shfl_sync(FULL, H.t, src);
                 const int bestTri = __shfl_sync(FULL, H.tri, src);
                 Hit L; L.t = bestT; L.tri = bestTri; L.z = L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
-                for (int k = (int)lane; k < ccount; k += 32) {
+                // two triangles per lane and step: six independent 128/64-bit loads in flight before the first test
+                int k = (int)lane;
+                for (; k + 32 < ccount; k += 64) {
+                    TriHot ta = loadTri(T, cstart + k), tb = loadTri(T, cstart + k + 32);
+                    float u, v, z;
+                    if (rayTriHit(O, D, ta.v0, ta.e1, ta.e2, u, v, z)) acceptHit(T, cstart + k, ta.canon, O, D, u, v, z, eps, true, L);
+                    if (rayTriHit(O, D, tb.v0, tb.e1, tb.e2, u, v, z)) acceptHit(T, cstart + k + 32, tb.canon, O, D, u, v, z, eps, true, L);
+                }
+                if (k < ccount) {
                     TriHot tr = loadTri(T, cstart + k);
                     float u, v, z;
-                    if (rayTri(O, D, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, true, L);
+                    if (rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, true, L);
                 }
                 const bool improved = L.t != bestT || L.tri != bestTri;
                 const unsigned im = __ballot_sync(FULL, improved);
@@ -365,7 +404,7 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                 for (int i = start; i < start + count; i++) {
                     TriHot tr = loadTri(T, i);
                     float u, v, z;
-                    if (rayTri(o, d, tr.v0, tr.e1, tr.e2, u, v, z) == 2) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
+                    if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
                 }
             }
             float zb = H.tri >= 0 ? fminf(H.z, zbound) : zbound;
