@@ -40,6 +40,15 @@ WORKLOADS = {
                 "scenes/cornell.txt + dragon_5.obj (12 500 tris, 2 645 nodes), 800x800, DEPTH 8, short-stack, AA+DOF, compaction + material sort"),
     "sphere": ("cornell_sphere_low_1.npz", 800, 800, "fullstack", {},
                "scenes/cornell.txt + sphere_low_1.obj (20 tris, 63 nodes), 800x800, DEPTH 8"),
+    # BASELINE configs[3]: synthetic ~1.6 M-triangle dragon (scenes/dragon.obj subdivided twice) in the cornell box, 1080p
+    "dragon1m": ("cornell_sphere_low_1.npz", 1920, 1080, "fullstack", {},
+                 "scenes/cornell.txt walls + scenes/dragon.obj subdivided 2x (1.6 M tris, scale 0.6), 1920x1080, DEPTH 8, full-stack"),
+}
+# traversal-only microbenchmarks (kdpt_trace): name -> (triangles, rays per GPU, description)   BASELINE configs[4]
+TRACE_WORKLOADS = {
+    "soup10m": (10_000_000, 1 << 24, "synthetic 10 M-triangle random soup (seed 12345), incoherent rays (origins uniform in the root box, "
+                "directions uniform on the sphere), traversal+intersection only, full-stack"),
+    "soup1m": (1_000_000, 1 << 24, "synthetic 1 M-triangle random soup (seed 12345), incoherent in-box rays, traversal only, full-stack"),
 }
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
@@ -103,6 +112,16 @@ def load_scene(workload: str):
     import kdtreepathtraceroptimization_b200 as kdpt
     fixture, w, h, mode, extra, desc = WORKLOADS[workload]
     sc = kdpt.Scene.from_npz(os.path.join(ROOT, "tests", "golden", fixture)).with_resolution(w, h).first_frame_camera()
+    if workload == "dragon1m":
+        from kdtreepathtraceroptimization_b200 import meshes
+        t18 = meshes.dense_dragon(os.path.join(ROOT, "tests", "golden", "dragon_100k.npz"), 2, 0.6)
+        tree = kdpt.Scene.from_triangles(t18)                     # the library's host-side KD builder (reference tree)
+        sc.nodes, sc.tris = tree.nodes, tree.tris
+        # dragon.mtl: illum 6 -> glass (REFL 1, REFR 1, ior 1.5), scene.cpp:748-760
+        m = sc.materials[-1:].copy()
+        m['color'] = 1.0; m['specular_exponent'] = 1.0; m['specular_color'] = 1.0; m['hasReflective'] = 1.0
+        m['hasRefractive'] = 1.0; m['indexOfRefraction'] = 1.5; m['transmittance'] = 0.0; m['emittance'] = 0.0
+        sc.materials = np.concatenate([sc.materials[:-1], m])
     params = kdpt.default_params(mode=kdpt.MODES[mode], **extra)
     return sc, params, desc
 
@@ -169,6 +188,106 @@ def algorithmic_bytes_per_ray(sc, params):
                 ray_bounces_iter1=int(tot))
 
 
+def run_trace_workload(args):
+    """BASELINE configs[4]: traversal-only microbenchmark, rays sharded in contiguous chunks, no collective."""
+    import torch
+    import torch.distributed as dist
+    import kdtreepathtraceroptimization_b200 as kdpt
+    from kdtreepathtraceroptimization_b200 import meshes
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    ntri, nrays, desc = TRACE_WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        nrays = 20000
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sc = kdpt.Scene.from_triangles(meshes.triangle_soup(ntri))
+    lo, hi = sc.nodes['mins'][0].astype('f8'), sc.nodes['maxs'][0].astype('f8')
+    rs = np.random.default_rng(777 + rank)
+    d = rs.normal(size=(nrays, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([lo + rs.random((nrays, 3)) * (hi - lo), d], 1).astype('f4')
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import KO_CTR, KO_HIT, KO_STACK_T1, KO_T1, P
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    O = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    cores = os.cpu_count() or 1
+
+    def cpu_run(mode, k):
+        out = np.zeros(k, KO_HIT); ctr = np.zeros(1, KO_CTR)
+        t0 = time.perf_counter()
+        O.ko_trace_batch(mode, P(sc.nodes), len(sc.nodes), P(sc.tris), len(sc.tris), 1, P(rays[:k]), k, None, P(out), P(ctr), cores)
+        return time.perf_counter() - t0, ctr[0]
+    W = max(args.warmup, 3); K = args.steps
+    if args.impl == "reference":
+        # the reference's traverseKDbare semantics (its own function overflows nodeIDs[4000] on this 32 767-node tree:
+        # SURVEY 8c) through the guarded restatement in the oracle
+        secs = 0.0
+        for k in range(K):
+            dt, _ = cpu_run(KO_T1, nrays); secs += dt
+        v = K * nrays / secs / 1e6
+        print(json.dumps({"impl": "reference", "metric": "Mrays/s (traverse+intersect)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
+                          "steps": K, "warmup": 0, "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "rays_per_step": nrays},
+                          "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": f"{nrays} rays per step"},
+                          "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    ctx = kdpt.Context(sc, device=local)
+    ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
+    d_rays = torch.from_numpy(rays).cuda(); d_hits = torch.zeros(nrays, 8, dtype=torch.float32, device="cuda")
+    for _ in range(W):
+        ctx.trace_device(d_rays.data_ptr(), None, nrays, d_hits.data_ptr(), kdpt.FULLSTACK, ts.cuda_stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    time.sleep(0.3)
+    clocks.rows.clear()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):           # 0.9 GB of tree + 0.9 GB of rays/hits per step >> 126 MB L2: no flush needed
+        evs[k][0].record(ts)
+        ctx.trace_device(d_rays.data_ptr(), None, nrays, d_hits.data_ptr(), kdpt.FULLSTACK, ts.cuda_stream)
+        evs[k][1].record(ts)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    hrays = torch.from_numpy(rays).pin_memory().numpy(); hhits = np.zeros(nrays, kdpt.HIT)
+    t0 = time.perf_counter()
+    for k in range(3):
+        kdpt._check(ctx._lib.kdpt_trace(ctx._h, hrays.ctypes.data, None, nrays, hhits.ctypes.data, kdpt.FULLSTACK), "kdpt_trace")
+    e2e_s = (time.perf_counter() - t0) / 3
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        value = world * nrays * K / (ms * 1e-3) / 1e6
+        dt, ctr = cpu_run(KO_STACK_T1, 20000)
+        V = float(ctr['nodes']) / 20000; T = float(ctr['tris']) / 20000
+        bpr = 48 + 16 * V + 52 * T
+        peak, peak_src = peak_hbm()
+        achieved = bpr * nrays / (ms / K * 1e-3) / 1e9
+        dt1, _ = cpu_run(KO_T1, 20000)
+        print(json.dumps({"metric": "Mrays/s (traverse+intersect)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
+                          "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": desc, "rays_per_step_per_gpu": nrays, "tree": ctx.tree_info(),
+                                                          "l2": "working set (tree 0.9 GB + rays/hits 0.9 GB) exceeds L2; no flush"},
+                          "clocks": clk, "gpu_launches": K,
+                          "e2e": {"value": world * nrays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": nrays * 24, "d2h_bytes_per_step": nrays * 32},
+                          "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                       "kernel": "traceKernel<fullstack>", "avg_launch_ms": ms / K, "algorithmic_bytes_per_ray": bpr,
+                                       "V_nodes_per_ray": V, "T_tris_per_ray": T, "peak_source": peak_src},
+                          "cpu_baseline": {"value": 20000 / dt1 / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                           "sample": "20 000 of the same rays through the reference's traverseKDbare semantics (oracle restatement)"}}), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -200,13 +319,16 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kdpt", choices=["kdpt", "reference"])
-    ap.add_argument("--workload", default="bunny", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="bunny", choices=sorted(WORKLOADS) + sorted(TRACE_WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload in TRACE_WORKLOADS:
+        run_trace_workload(args)
+        return
     if args.impl == "reference":
         if args.steps > 8:
             args.steps = 8          # one step = one full 800x800 sample on the CPU; keep the arm within minutes
@@ -245,6 +367,7 @@ def main():
                 total_img.copy_(img, non_blocking=True)
                 dist.all_reduce(total_img)
 
+    clocks = ClockSampler(local)            # nvidia-smi needs ~100 ms to start: launch it before the warm-up
     with torch.cuda.stream(ts):
         for k in range(W):
             flush.fill_(k & 0xff)
@@ -254,7 +377,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     rb0, l0 = ctx.counters()
-    clocks = ClockSampler(local)
+    clocks.rows.clear()                     # keep only the samples taken during the timed region
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     with torch.cuda.stream(ts):
         for k in range(K):

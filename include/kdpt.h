@@ -137,6 +137,23 @@ const char* kdpt_last_error(void);
  * main.cpp:1111-1129). Pure host arithmetic; call it on the camera the scene loader produced. */
 void kdpt_camera_first_frame(kdpt_camera* camera);
 
+/* ---- host side: the reference's scene / OBJ loading and KD build (src/scene.cpp, KDtree.cpp, KDnode.cpp, objmesh.cpp +
+ * tinyobjloader v1.0.0) — pure host code, produces exactly the arrays above, byte-identical to the reference loader's. */
+typedef struct kdpt_host_scene kdpt_host_scene;
+/* Scene(txt) + Scene::loadObj(obj, mtl_dir) (main.cpp:1031-1033). obj_path may be NULL (no mesh); mtl_dir NULL = the
+ * OBJ's directory (main.cpp:1033); kd_depth <= 0 = the reference's literal 13 (scene.cpp:872). synth_normals != 0
+ * generates area-weighted vertex normals for OBJs without one `vn` per `v` (the reference reads out of bounds there). */
+int kdpt_scene_load(const char* scene_txt, const char* obj_path, const char* mtl_dir, int kd_depth, int synth_normals,
+                    kdpt_host_scene** out);
+/* KDtree(triangles) -> updateBbox -> split(kd_depth) -> flatten, for a caller-supplied triangle list:
+ * tri18 = x1 y1 z1 x2 y2 z2 x3 y3 z3 nx1 ny1 nz1 nx2 ny2 nz2 nx3 ny3 nz3 per triangle, mtl = shape index per triangle or NULL */
+int kdpt_scene_from_triangles(const float* tri18, const int* mtl, int n, int kd_depth, kdpt_host_scene** out);
+/* borrow the arrays (valid until kdpt_scene_free) */
+int kdpt_scene_view(const kdpt_host_scene* scene, kdpt_scene* view, int* iterations);
+/* source triangle (OBJ face order) of every TriBare entry */
+const int* kdpt_scene_triangle_sources(const kdpt_host_scene* scene);
+void kdpt_scene_free(kdpt_host_scene* scene);
+
 /* pathtraceInit: flatten + upload. device = CUDA ordinal. The host arrays are not retained. */
 int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out);
 /* pathtraceFree */

@@ -105,6 +105,13 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_bounce.argtypes = [vp, ci, ci, ctypes.POINTER(CParams), vp, ci, vp, ci]
     lib.kdpt_camera_first_frame.argtypes = [vp]
     lib.kdpt_camera_first_frame.restype = None
+    lib.kdpt_scene_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ci, ci, ctypes.POINTER(vp)]
+    lib.kdpt_scene_from_triangles.argtypes = [vp, vp, ci, ci, ctypes.POINTER(vp)]
+    lib.kdpt_scene_view.argtypes = [vp, ctypes.POINTER(_CScene), ctypes.POINTER(ci)]
+    lib.kdpt_scene_triangle_sources.argtypes = [vp]
+    lib.kdpt_scene_triangle_sources.restype = ctypes.POINTER(ctypes.c_int)
+    lib.kdpt_scene_free.argtypes = [vp]
+    lib.kdpt_scene_free.restype = None
     lib.kdpt_clear_image.argtypes = [vp]
     lib.kdpt_set_stream.argtypes = [vp, vp]
     lib.kdpt_bind_image.argtypes = [vp, vp]
@@ -142,6 +149,45 @@ class Scene:
                      materials=np.ascontiguousarray(z['materials']), offsets=np.ascontiguousarray(z['offsets'], dtype='i4'),
                      camera=np.ascontiguousarray(z['camera']), trace_depth=int(z['trace_depth']),
                      iterations=int(z['iterations']) if 'iterations' in z else 0)
+
+    @staticmethod
+    def _from_host(h) -> "Scene":
+        lib = load_library()
+        v = _CScene(); it = ctypes.c_int()
+        _check(lib.kdpt_scene_view(h, ctypes.byref(v), ctypes.byref(it)), "kdpt_scene_view")
+
+        def arr(ptr, n, dt):
+            if not ptr or n == 0:
+                return np.zeros(0, dt)
+            return np.frombuffer(ctypes.string_at(ptr, n * dt.itemsize), dtype=dt).copy()
+        cam = np.frombuffer(bytes(v.camera), dtype=CAMERA).copy()
+        sc = Scene(nodes=arr(v.nodes, v.numNodes, NODE), tris=arr(v.tris, v.numTris, TRI), geoms=arr(v.geoms, v.numGeoms, GEOM),
+                   materials=arr(v.materials, v.numMaterials, MATERIAL), offsets=arr(v.objMaterialOffsets, v.numShapes, np.dtype('i4')),
+                   camera=cam, trace_depth=int(v.traceDepth), iterations=int(it.value))
+        src = lib.kdpt_scene_triangle_sources(h)
+        sc.tri_source = np.ctypeslib.as_array(src, (v.numTris,)).copy() if v.numTris else np.zeros(0, 'i4')
+        lib.kdpt_scene_free(h)
+        return sc
+
+    @staticmethod
+    def load(scene_txt: str, obj_path: str | None = None, mtl_dir: str | None = None, kd_depth: int = 13,
+             synth_normals: bool = False) -> "Scene":
+        """the reference's `Scene(txt)` + `loadObj(obj)` through the library's host loader (kdpt_scene_load)"""
+        h = ctypes.c_void_p()
+        _check(load_library().kdpt_scene_load(scene_txt.encode(), obj_path.encode() if obj_path else None,
+                                              mtl_dir.encode() if mtl_dir else None, kd_depth, int(synth_normals),
+                                              ctypes.byref(h)), "kdpt_scene_load")
+        return Scene._from_host(h)
+
+    @staticmethod
+    def from_triangles(tri18: np.ndarray, mtl: np.ndarray | None = None, kd_depth: int = 13) -> "Scene":
+        """KD build + flatten of a triangle list (n x 18 float32) with the library's host builder"""
+        tri18 = np.ascontiguousarray(tri18, dtype=np.float32).reshape(-1, 18)
+        m = np.ascontiguousarray(mtl, dtype=np.int32) if mtl is not None else None
+        h = ctypes.c_void_p()
+        _check(load_library().kdpt_scene_from_triangles(_ptr(tri18), _ptr(m) if m is not None else None, len(tri18), kd_depth,
+                                                        ctypes.byref(h)), "kdpt_scene_from_triangles")
+        return Scene._from_host(h)
 
     def first_frame_camera(self) -> "Scene":
         """apply the reference's main.cpp camera set-up (kdpt_camera_first_frame) and return self"""

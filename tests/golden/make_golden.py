@@ -163,6 +163,23 @@ def one(scene, obj, out, nrays):
           "T2 hits", int(res['ref_T2_hit'].sum()), os.path.getsize(out) // 1024, "KiB")
 
 
+def dragon_fixture():
+    """scenes/dragon.obj (50 000 v / 100 000 f, no vn) as a compact array fixture: the seed mesh of the synthetic
+    ~1.6 M-triangle dragon of BASELINE config 4 (kdtreepathtraceroptimization_b200.meshes.dense_dragon)."""
+    v, f = [], []
+    for l in open(f"{REF}/scenes/dragon.obj"):
+        p = l.split()
+        if not p:
+            continue
+        if p[0] == 'v':
+            v.append([float(x) for x in p[1:4]])
+        elif p[0] == 'f':
+            idx = [int(t.split('/')[0]) - 1 for t in p[1:]]
+            for k in range(1, len(idx) - 1):
+                f.append([idx[0], idx[k], idx[k + 1]])
+    np.savez_compressed(os.path.join(HERE, "dragon_100k.npz"), verts=np.array(v, 'f4'), faces=np.array(f, 'i4'))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         one(sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]))
@@ -173,3 +190,7 @@ if __name__ == "__main__":
         import shutil
         shutil.copy(f"{REF}/rnd/houdini/data", os.path.join(HERE, "houdini_data.txt"))
         shutil.copy(f"{REF}/rnd/houdini/dataout", os.path.join(HERE, "houdini_dataout.txt"))
+        os.makedirs(os.path.join(HERE, "scenes"), exist_ok=True)
+        for name in ("cornell.txt", "cornell8.txt", "sphere_low_1.obj", "sphere.mtl", "stanford_bunny.obj", "stanford_bunny.mtl", "dragon.mtl"):
+            shutil.copy(f"{REF}/scenes/{name}", os.path.join(HERE, "scenes", name))
+        dragon_fixture()

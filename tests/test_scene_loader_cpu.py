@@ -1,0 +1,71 @@
+"""CPU-only: the product's host-side scene / OBJ loader and KD builder (csrc/kdpt_scene.cpp, pure host code) against
+the arrays dumped from the UNMODIFIED reference loader (tests/golden/*.npz) — byte-for-byte — and against the oracle's
+builder on random triangle soups."""
+import os
+
+import numpy as np
+import pytest
+
+import kdtreepathtraceroptimization_b200 as kdpt
+from conftest import GOLDEN
+
+SCENES = os.path.join(GOLDEN, "scenes")
+CASES = [("cornell.txt", "sphere_low_1.obj", "cornell_sphere_low_1.npz", SCENES),
+         ("cornell8.txt", "stanford_bunny.obj", "cornell8_stanford_bunny.npz", SCENES),
+         ("cornell.txt", "dragon_5.obj", "cornell_dragon_5.npz", "/root/reference/scenes")]
+
+
+@pytest.mark.parametrize("txt,obj,gold,base", CASES)
+def test_loader_reproduces_the_reference_loader_byte_for_byte(txt, obj, gold, base):
+    """Scene(txt) + loadObj(obj): materials, geoms (transform / inverse / inverse-transpose through glm's exact
+    operation order), camera, per-shape OBJ materials, tinyobj's own decimal parser, KD build and flatten"""
+    if not os.path.exists(os.path.join(base, obj)):
+        pytest.skip(f"{obj} lives only in the reference checkout")
+    s = kdpt.Scene.load(os.path.join(base, txt), os.path.join(base, obj))
+    g = np.load(os.path.join(GOLDEN, gold))
+    for name in ("nodes", "tris", "geoms", "materials"):
+        assert getattr(s, name).tobytes() == g[name].tobytes(), name
+    assert (s.offsets == g['offsets']).all()
+    assert s.camera.tobytes() == g['camera'].tobytes()          # includes the NaN `right` of scene.cpp:221
+    assert s.trace_depth == int(g['trace_depth']) and s.iterations == int(g['iterations'])
+
+
+def test_builder_equals_oracle_builder_on_random_soups(oracle):
+    rng = np.random.default_rng(3)
+    for n, depth in ((0, 13), (1, 13), (2, 13), (3, 13), (500, 13), (20000, 13), (3000, 4), (3000, 30)):
+        c = rng.uniform(-1, 1, (n, 3)); e1 = rng.uniform(-.1, .1, (n, 3)); e2 = rng.uniform(-.1, .1, (n, 3))
+        t18 = np.concatenate([c, c + e1, c + e2, rng.normal(size=(n, 9))], 1).astype('f4')
+        mtl = rng.integers(0, 3, n).astype('i4')
+        s = kdpt.Scene.from_triangles(t18, mtl, depth)
+        on, ot, src = oracle.build_tree(t18, mtl, depth)
+        assert s.nodes.tobytes() == on.tobytes() and s.tris.tobytes() == ot.tobytes(), (n, depth)
+        assert (s.tri_source == src).all()
+
+
+def test_houdini_fixture_through_the_product_builder(tmp_path):
+    """the reference's own golden vector (rnd/houdini/data -> dataout, split(30)) through the product's builder"""
+    vals = np.array([float(l) for l in open(os.path.join(GOLDEN, "houdini_data.txt")).read().split()], 'f4').reshape(-1, 9)
+    t18 = np.concatenate([vals, np.zeros_like(vals)], 1)
+    s = kdpt.Scene.from_triangles(t18, None, 30)
+    lines = ["%g %g %g %g %g %g" % (*n['mins'], *n['maxs']) for n in s.nodes]
+    assert "\n".join(lines) + "\n" == open(os.path.join(GOLDEN, "houdini_dataout.txt")).read()
+
+
+def test_loader_errors_and_normal_synthesis(tmp_path):
+    with pytest.raises(kdpt.KdptError, match="cannot open"):
+        kdpt.Scene.load(str(tmp_path / "nope.txt"))
+    obj = tmp_path / "quad.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    txt = os.path.join(SCENES, "cornell.txt")
+    with pytest.raises(kdpt.KdptError, match="normals"):
+        kdpt.Scene.load(txt, str(obj))
+    s = kdpt.Scene.load(txt, str(obj), synth_normals=True)
+    assert len(s.tris) == 2 and len(s.nodes) == 1                  # fan triangulation, <= 2 triangles -> one leaf
+    assert np.allclose([s.tris['nz1'], s.tris['nz2'], s.tris['nz3']], 1.0)
+    assert len(s.materials) == 6 and s.offsets.tolist() == [5]     # default white material appended for the shape
+    with pytest.raises(kdpt.KdptError, match="vertex"):
+        bad = tmp_path / "bad.obj"
+        bad.write_text("v 0 0 0\nvn 0 0 1\nf 1 2 3\n")
+        kdpt.Scene.load(txt, str(bad))
+    only = kdpt.Scene.load(txt)                                     # scene without a mesh
+    assert len(only.nodes) == 0 and len(only.geoms) == 6

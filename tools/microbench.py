@@ -11,24 +11,11 @@ ap.add_argument("--rays", type=int, default=1 << 22)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--modes", default="fullstack,shortstack,ref_t1,ref_t2")
 ap.add_argument("--cls", default="inside")
-ap.add_argument("--soup", type=int, default=0, help="synthetic N-triangle soup (tree built by the CPU oracle: dev tool only)")
+ap.add_argument("--soup", type=int, default=0, help="synthetic N-triangle soup (kdtreepathtraceroptimization_b200.meshes), tree from the library host builder")
 args = ap.parse_args()
 if args.soup:
-    import ctypes
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-    from conftest import Oracle
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle"), "liboracle.so"])
-    orc = Oracle(ctypes.CDLL(os.path.join(root, "oracle", "liboracle.so")))
-    rs = np.random.default_rng(12345)
-    N = args.soup
-    r = 0.01 * (1e6 / N) ** (1 / 3) if N > 1e6 else 0.01
-    c = rs.uniform(-1, 1, (N, 3)); e1 = rs.uniform(-r, r, (N, 3)); e2 = rs.uniform(-r, r, (N, 3))
-    nrm = np.cross(e1, e2); nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
-    t18 = np.concatenate([c, c + e1, c + e2, nrm, nrm, nrm], 1).astype('f4')
-    t0 = time.time(); nodes, tris, _ = orc.build_tree(t18, None, 13); print("oracle build %.1fs" % (time.time() - t0))
-    sc = kdpt.Scene.tree_only(nodes, tris)
+    from kdtreepathtraceroptimization_b200 import meshes
+    t0 = time.time(); sc = kdpt.Scene.from_triangles(meshes.triangle_soup(args.soup)); print("host build %.1fs" % (time.time() - t0))
 else:
     sc = kdpt.Scene.from_npz(args.scene)
 ctx = kdpt.Context(sc, 0)
