@@ -177,6 +177,9 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     if ((rc = upload(ctx->treeMem[6], flat.nrmA, (const HostF4**)&T.nrmA, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[7], flat.nrmB, (const HostF4**)&T.nrmB, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[8], flat.nrmC, (const HostF2**)&T.nrmC, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[9], flat.triOrig, &T.triOrig, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[10], flat.chunkLo, (const HostF4**)&T.chunkLo, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[11], flat.chunkHi, (const HostF4**)&T.chunkHi, s))) return fail(rc);
     T.numNodes = flat.numNodes; T.numTris = flat.numTris;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = flat.rootLo[a]; T.rootHi[a] = flat.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = flat.tagCand[k];
@@ -204,7 +207,8 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     flat.boxHi.clear(); flat.boxHi.shrink_to_fit(); flat.triA.clear(); flat.triA.shrink_to_fit();
     flat.triB.clear(); flat.triB.shrink_to_fit(); flat.triC.clear(); flat.triC.shrink_to_fit();
     flat.nrmA.clear(); flat.nrmA.shrink_to_fit(); flat.nrmB.clear(); flat.nrmB.shrink_to_fit();
-    flat.nrmC.clear(); flat.nrmC.shrink_to_fit();
+    flat.nrmC.clear(); flat.nrmC.shrink_to_fit(); flat.triOrig.clear(); flat.triOrig.shrink_to_fit();
+    flat.chunkLo.clear(); flat.chunkLo.shrink_to_fit(); flat.chunkHi.clear(); flat.chunkHi.shrink_to_fit();
     ctx->info = flat;
     *out = ctx;
     return KDPT_OK;

@@ -35,12 +35,13 @@ namespace kdpt {
 constexpr int kMaxDepth = 32;           // deepest tree the per-ray stacks accept (reference: split(13) -> 14)
 constexpr float kExitSlack = 1e-3f;     // early-exit slack in world units (acceptance is on the nudged distance)
 constexpr unsigned kLeafFlag = 3u;
+constexpr unsigned kNoChunks = 0xffffffffu;
 
 // ---- flattened tree in HBM -------------------------------------------------------------------------------------
 // node (16 B, index == reference node ID, IDs are DFS pre-order):
 //   interior: x = split plane (float bits) = nodes[left].maxs[axis]   y = right child   z = left child
 //             w = axis (bits 0-1) | (parent + 1) << 2
-//   leaf:     x = first leaf triangle            y = triangle count (may be 0)          z = unused
+//   leaf:     x = first leaf triangle            y = triangle count (may be 0)          z = first chunk or ~0u
 //             w = 3 | (parent + 1) << 2
 // leaf triangles keep the reference's leaf order (TriBare index i), split into a hot and a cold part:
 //   triA[i] = (v0.x, v0.y, v0.z, e1.x)  triB[i] = (e1.y, e1.z, e2.x, e2.y)  triC[i] = (e2.z, canonical index)
@@ -57,6 +58,9 @@ struct Tree {
     const float4* nrmA;
     const float4* nrmB;
     const float2* nrmC;
+    const int* triOrig;      // TriBare index of entry i (entries of chunked leaves are Morton-reordered)
+    const float4* chunkLo;   // padded AABBs of the 32-entry chunks of chunked leaves (leaf record .z = first chunk)
+    const float4* chunkHi;
     int numNodes;
     int numTris;
     float rootLo[3], rootHi[3];
@@ -171,25 +175,46 @@ KDPT_HD TriHot loadTri(const Tree& T, int i)
     return t;
 }
 
-// Leaf body after glm said "intersected": interpolated normal, nudged point, distance, acceptance.
-// tieByIndex: equal distance keeps the smaller canonical index (order-independent closest hit).
-KDPT_HD void acceptHit(const Tree& T, int i, int canon, V3 o, V3 d, float u, float v, float z, float eps,
-                       bool tieByIndex, Hit& H)
+// Leaf body after glm said "intersected": interpolated normal, nudged point, distance, acceptance
+// (`t > 0 && t_min > t`, pathtrace.cu:1000). Equal distances: the candidate also wins when tieBest >= 0 and
+// tieKey < tieBest — the order-independent form of "first in the reference's order wins" (the exact modes key on the
+// canonical index, the reference-compatible ones on the TriBare index within the current leaf). Returns accepted.
+KDPT_HD bool acceptHit(const Tree& T, int i, int canon, V3 o, V3 d, float u, float v, float z, float eps,
+                       int tieKey, int tieBest, Hit& H)
 {
     float4 a = KDPT_LDG(T.nrmA + i), b = KDPT_LDG(T.nrmB + i);
     float2 c = KDPT_LDG(T.nrmC + i);
     V3 n1 = mk(a.x, a.y, a.z), n2 = mk(a.w, b.x, b.y), n3 = mk(b.z, b.w, c.x);
     int mtl = __float_as_int(c.y);
-    H.anyMtl = mtl;
     V3 hp = o + d * z;
     V3 nrm = normalize(((1 - u - v) * n1 + u * n2) + v * n3);
     hp = hp + nrm * eps;
     float t = length(hp - o);
-    bool better = t > 0.0f && H.t > t;
-    if (tieByIndex && !better && H.tri >= 0 && t > 0.0f && H.t == t && canon < H.tri) better = true;
+    bool better = t > 0.0f && (H.t > t || (H.t == t && tieBest >= 0 && tieKey < tieBest));
     if (better) {
         H.t = t; H.z = z; H.u = u; H.v = v; H.tri = canon; H.nx = nrm.x; H.ny = nrm.y; H.nz = nrm.z; H.mtl = mtl;
     }
+    return better;
+}
+
+// ray (line) against the padded box of chunk c: entry / exit parameters. NaNs (0 * inf) drop out of fminf/fmaxf,
+// which only widens the interval.
+KDPT_HD void chunkInterval(const Tree& T, int c, V3 o, V3 inv, float& tn, float& tf)
+{
+    float4 lo = KDPT_LDG(T.chunkLo + c), hi = KDPT_LDG(T.chunkHi + c);
+    float v1 = (lo.x - o.x) * inv.x, v2 = (hi.x - o.x) * inv.x;
+    float v3 = (lo.y - o.y) * inv.y, v4 = (hi.y - o.y) * inv.y;
+    float v5 = (lo.z - o.z) * inv.z, v6 = (hi.z - o.z) * inv.z;
+    tn = fmaxf(fmaxf(fminf(v1, v2), fminf(v3, v4)), fminf(v5, v6));
+    tf = fminf(fminf(fmaxf(v1, v2), fmaxf(v3, v4)), fmaxf(v5, v6));
+}
+// exact modes: a chunk can be skipped when the ray misses its box, leaves it behind the origin, or enters it beyond
+// the best hit so far (zlim = best glm t + slack). Written so that any NaN keeps the chunk.
+KDPT_HD bool chunkMayHit(const Tree& T, int c, V3 o, V3 inv, float zlim, float slack)
+{
+    float tn, tf;
+    chunkInterval(T, c, o, inv, tn, tf);
+    return !(tn > tf) && !(tf < -slack) && !(tn > zlim);
 }
 
 KDPT_HD void initHit(Hit& H, float tMinIn)
@@ -263,11 +288,21 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
         }
         int start = (int)nd.x, count = (int)nd.y;
         if (count > 0) {
-            if (COUNT) { ctr->leaves++; ctr->tris += (unsigned)count; }
-            for (int i = start; i < start + count; i++) {
-                TriHot tr = loadTri(T, i);
-                float u, v, z;
-                if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
+            if (COUNT) ctr->leaves++;
+            const int nch = nd.z != kNoChunks ? (count + 31) >> 5 : 1;
+            for (int c = 0; c < nch; c++) {
+                int b = start, e = start + count;
+                if (nd.z != kNoChunks) {
+                    float zl = (H.tri >= 0 ? fminf(H.z, zbound) : zbound) + slack;
+                    if (!chunkMayHit(T, (int)nd.z + c, o, inv, zl, slack)) continue;
+                    b = start + 32 * c; e = b + 32 < start + count ? b + 32 : start + count;
+                }
+                if (COUNT) ctr->tris += (unsigned)(e - b);
+                for (int i = b; i < e; i++) {
+                    TriHot tr = loadTri(T, i);
+                    float u, v, z;
+                    if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, tr.canon, H.tri, H);
+                }
             }
         }
         float zb = H.tri >= 0 ? fminf(H.z, zbound) : zbound;
@@ -323,8 +358,43 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
     }
     RayStack<STACK> st; st.clear();
     unsigned cur = 0; float tmin = t0, tmax = t1;
+
+    // one owner's leaf range [cstart, cstart+ccount) tested by the whole warp; L = lane-local best candidate
+    auto testRange = [&](V3 O, V3 D, int cstart, int kbeg, int kend, Hit& L) {
+        int k = kbeg + (int)lane;
+        for (; k + 32 < kend; k += 64) {      // two triangles per lane and step: six independent loads in flight
+            TriHot ta = loadTri(T, cstart + k), tb = loadTri(T, cstart + k + 32);
+            float u, v, z;
+            if (rayTriHit(O, D, ta.v0, ta.e1, ta.e2, u, v, z)) acceptHit(T, cstart + k, ta.canon, O, D, u, v, z, eps, ta.canon, L.tri, L);
+            if (rayTriHit(O, D, tb.v0, tb.e1, tb.e2, u, v, z)) acceptHit(T, cstart + k + 32, tb.canon, O, D, u, v, z, eps, tb.canon, L.tri, L);
+        }
+        if (k < kend) {
+            TriHot tr = loadTri(T, cstart + k);
+            float u, v, z;
+            if (rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, tr.canon, L.tri, L);
+        }
+    };
+    // best candidate of the warp (min nudged t, ties to the smaller canonical index) back to the owner lane
+    auto reduceToOwner = [&](int src, float bestT, int bestTri, const Hit& L) {
+        const bool improved = L.t != bestT || L.tri != bestTri;
+        if (!__ballot_sync(FULL, improved)) return;
+        float kt = improved ? L.t : FLT_MAX; int kc = improved ? L.tri : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            float t2 = __shfl_xor_sync(FULL, kt, off); int c2 = __shfl_xor_sync(FULL, kc, off);
+            if (t2 < kt || (t2 == kt && c2 < kc)) { kt = t2; kc = c2; }
+        }
+        const int win = __ffs(__ballot_sync(FULL, improved && L.t == kt && L.tri == kc)) - 1;
+        Hit W;
+        W.t = kt; W.tri = kc;
+        W.z = __shfl_sync(FULL, L.z, win); W.u = __shfl_sync(FULL, L.u, win); W.v = __shfl_sync(FULL, L.v, win);
+        W.nx = __shfl_sync(FULL, L.nx, win); W.ny = __shfl_sync(FULL, L.ny, win); W.nz = __shfl_sync(FULL, L.nz, win);
+        W.mtl = __shfl_sync(FULL, L.mtl, win); W.anyMtl = W.mtl;
+        if ((int)lane == src) H = W;
+    };
+
     while (__any_sync(FULL, run)) {
-        int start = 0, count = 0;
+        int start = 0, count = 0; unsigned chunk0 = kNoChunks;
         if (run) {
             uint4 nd = __ldg(T.nodes + cur);
             while ((nd.w & 3u) != kLeafFlag) {
@@ -339,17 +409,59 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                 else { st.push(farc, tp, tmax); cur = nearc; tmax = tp; }
                 nd = __ldg(T.nodes + cur);
             }
-            start = (int)nd.x; count = (int)nd.y;
+            start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
         }
-        // ---- fat leaves: the whole warp works for one owner at a time ----
-        // Which pending leaves are worth it is decided per round with a small cost model: testing a leaf of c triangles
-        // cooperatively costs about 1.5 + c/32 steps (broadcast + reduction + ceil(c/32) tests), while the lane-private
-        // pass that follows costs max(c) over the lanes left to it. Taking the group of near-largest leaves (within
-        // 3/4 of the largest, g lanes) out of the private pass pays when g * (1.5 + m1/32) < a * (m1 - m2), m2 being the
-        // largest leaf that would remain and a = laneCost32/32 the relative cost of a lane-private step (its loads are
-        // scattered over 32 leaves; ~1 when the triangles sit in L1, larger when every lane pulls its own lines from L2). A warp whose lanes all sit in similar leaves therefore stays lane-private,
-        // a warp with one 986-triangle leaf among 20-triangle ones handles just that one together.
         bool pendingLeaf = run && count > 0;
+
+        // ---- chunked (fat) leaves: always cooperative. The lanes first test the owner's ray against 32 chunk boxes
+        // at a time, then the warp streams only the chunks the ray can touch. ----
+        unsigned chunked = __ballot_sync(FULL, pendingLeaf && chunk0 != kNoChunks);
+        if (pendingLeaf && chunk0 != kNoChunks) pendingLeaf = false;
+        while (chunked) {
+            const int src = __ffs(chunked) - 1;
+            chunked &= chunked - 1;
+            V3 O = mk(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
+            V3 D = mk(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
+            V3 INV = mk(__shfl_sync(FULL, inv.x, src), __shfl_sync(FULL, inv.y, src), __shfl_sync(FULL, inv.z, src));
+            const int cstart = __shfl_sync(FULL, start, src), ccount = __shfl_sync(FULL, count, src);
+            const int cchunk0 = (int)__shfl_sync(FULL, chunk0, src);
+            const float bestT = __shfl_sync(FULL, H.t, src);
+            const int bestTri = __shfl_sync(FULL, H.tri, src);
+            const float cslack = __shfl_sync(FULL, slack, src);
+            float zlim = __shfl_sync(FULL, (H.tri >= 0 ? fminf(H.z, zbound) : zbound) + slack, src);
+            Hit L; L.t = bestT; L.tri = bestTri; L.z = FLT_MAX; L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
+            const int nch = (ccount + 31) >> 5;
+            for (int cb = 0; cb < nch; cb += 32) {
+                const int c = cb + (int)lane;
+                unsigned hitMask = __ballot_sync(FULL, c < nch && chunkMayHit(T, cchunk0 + c, O, INV, zlim, cslack));
+                if (!hitMask) continue;
+                while (hitMask) {
+                    const int j = __ffs(hitMask) - 1;
+                    hitMask &= hitMask - 1;
+                    const int k = (cb + j) * 32 + (int)lane;
+                    if (k < ccount) {
+                        TriHot tr = loadTri(T, cstart + k);
+                        float u, v, z;
+                        if (rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, tr.canon, L.tri, L);
+                    }
+                }
+                // tighten the cull distance with whatever any lane has found so far (only worth it on long leaves)
+                if (cb + 32 < nch) {
+                    float lz = (L.t != bestT || L.tri != bestTri) ? L.z : FLT_MAX;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) lz = fminf(lz, __shfl_xor_sync(FULL, lz, off));
+                    if (lz < FLT_MAX) zlim = fminf(zlim, lz + cslack);
+                }
+            }
+            reduceToOwner(src, bestT, bestTri, L);
+        }
+
+        // ---- small leaves: per-round cost model. Testing a leaf of c triangles cooperatively costs about
+        // 1.5 + c/32 steps (broadcast + reduction + ceil(c/32) tests); the lane-private pass that follows costs max(c)
+        // over the lanes left to it, times a = laneCost32/32 (a lane-private step gathers from 32 different leaves:
+        // ~1 when the triangles sit in L1, larger when every lane pulls its own lines from L2). Taking the group of
+        // near-largest leaves (within 3/4 of the largest, g lanes) out of the private pass pays when
+        // g * (1.5 + m1/32) < a * (m1 - m2), m2 being the largest leaf that would remain. ----
         for (;;) {
             const int m1 = __reduce_max_sync(FULL, pendingLeaf ? count : 0);
             if (m1 < COOP_MIN) break;
@@ -367,36 +479,8 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                 const float bestT = __shfl_sync(FULL, H.t, src);
                 const int bestTri = __shfl_sync(FULL, H.tri, src);
                 Hit L; L.t = bestT; L.tri = bestTri; L.z = L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
-                // two triangles per lane and step: six independent 128/64-bit loads in flight before the first test
-                int k = (int)lane;
-                for (; k + 32 < ccount; k += 64) {
-                    TriHot ta = loadTri(T, cstart + k), tb = loadTri(T, cstart + k + 32);
-                    float u, v, z;
-                    if (rayTriHit(O, D, ta.v0, ta.e1, ta.e2, u, v, z)) acceptHit(T, cstart + k, ta.canon, O, D, u, v, z, eps, true, L);
-                    if (rayTriHit(O, D, tb.v0, tb.e1, tb.e2, u, v, z)) acceptHit(T, cstart + k + 32, tb.canon, O, D, u, v, z, eps, true, L);
-                }
-                if (k < ccount) {
-                    TriHot tr = loadTri(T, cstart + k);
-                    float u, v, z;
-                    if (rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, true, L);
-                }
-                const bool improved = L.t != bestT || L.tri != bestTri;
-                const unsigned im = __ballot_sync(FULL, improved);
-                if (im) {
-                    float kt = improved ? L.t : FLT_MAX; int kc = improved ? L.tri : 0x7fffffff;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        float t2 = __shfl_xor_sync(FULL, kt, off); int c2 = __shfl_xor_sync(FULL, kc, off);
-                        if (t2 < kt || (t2 == kt && c2 < kc)) { kt = t2; kc = c2; }
-                    }
-                    const int win = __ffs(__ballot_sync(FULL, improved && L.t == kt && L.tri == kc)) - 1;
-                    Hit W;
-                    W.t = kt; W.tri = kc;
-                    W.z = __shfl_sync(FULL, L.z, win); W.u = __shfl_sync(FULL, L.u, win); W.v = __shfl_sync(FULL, L.v, win);
-                    W.nx = __shfl_sync(FULL, L.nx, win); W.ny = __shfl_sync(FULL, L.ny, win); W.nz = __shfl_sync(FULL, L.nz, win);
-                    W.mtl = __shfl_sync(FULL, L.mtl, win); W.anyMtl = W.mtl;
-                    if ((int)lane == src) H = W;
-                }
+                testRange(O, D, cstart, 0, ccount, L);
+                reduceToOwner(src, bestT, bestTri, L);
             }
         }
         if (run) {
@@ -404,7 +488,7 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                 for (int i = start; i < start + count; i++) {
                     TriHot tr = loadTri(T, i);
                     float u, v, z;
-                    if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, true, H);
+                    if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, tr.canon, H.tri, H);
                 }
             }
             float zb = H.tri >= 0 ? fminf(H.z, zbound) : zbound;
@@ -461,18 +545,47 @@ KDPT_HD void traceRef(const Tree& T, V3 o, V3 d, float tMinIn, Hit& H, float* la
                 if ((nd.w & 3u) == kLeafFlag) {
                     int start = (int)nd.x, count = (int)nd.y;
                     int parent = (int)(nd.w >> 2) - 1;
-                    for (int i = start; i < start + count; i++) {
-                        TriHot tr = loadTri(T, i);
-                        int r = rayTri(o, d, tr.v0, tr.e1, tr.e2, bu, bv, bz);
-                        if (r == 2) {
-                            if (T2) {
-                                int k = tagged(parent) ? 1 : 0;
-                                if (k < T.numNodes) {
-                                    int bit = k * 2 + (leftFirst ? 1 : 0);
-                                    if (T.tagCand[bit] >= 0) tagMask |= 1u << bit;
-                                }
+                    // The reference walks the leaf in TriBare order and three things depend on that order: bary.z
+                    // is what the LAST triangle that got through the barycentric tests wrote (pathtrace.cu:951 prunes
+                    // on it), objMaterialIdx comes from the LAST glm hit (:991), and among equal nudged distances the
+                    // FIRST hit stays (strict `t_min > t`, :1000). All three are recovered from the entries' TriBare
+                    // indices (triOrig), so the entries may be visited in any order and whole chunks whose box the
+                    // ray's LINE misses can be skipped: a triangle writes bary.z only if the line pierces it (glm
+                    // writes z before rejecting t < 0, so no culling on the sign or size of t here).
+                    int zOrig = -1, mtlOrig = -1, accOrig = -1, nHits = 0;
+                    float zNew = bz;
+                    const int nch = nd.z != kNoChunks ? (count + 31) >> 5 : 1;
+                    for (int c = 0; c < nch; c++) {
+                        int b = start, e = start + count;
+                        if (nd.z != kNoChunks) {
+                            float tn, tf;
+                            chunkInterval(T, (int)nd.z + c, o, inv, tn, tf);
+                            if (tn > tf) continue;
+                            b = start + 32 * c; e = b + 32 < start + count ? b + 32 : start + count;
+                        }
+                        for (int i = b; i < e; i++) {
+                            TriHot tr = loadTri(T, i);
+                            float u, v, z;
+                            int r = rayTri(o, d, tr.v0, tr.e1, tr.e2, u, v, z);
+                            if (r == 0) continue;
+                            const int orig = KDPT_LDG(T.triOrig + i);
+                            if (orig > zOrig) { zOrig = orig; zNew = z; bu = u; bv = v; }
+                            if (r == 2) {
+                                nHits++;
+                                if (acceptHit(T, i, tr.canon, o, d, u, v, z, eps, orig, accOrig, H)) accOrig = orig;
+                                if (orig > mtlOrig) { mtlOrig = orig; H.anyMtl = __float_as_int(KDPT_LDG(T.nrmC + i).y); }
                             }
-                            acceptHit(T, i, tr.canon, o, d, bu, bv, bz, eps, false, H);
+                        }
+                    }
+                    bz = zNew;
+                    if (T2) {
+                        // "skip other side" (:1136/:1199) runs once per glm hit; its effect saturates after two
+                        for (int h = 0; h < (nHits < 2 ? nHits : 2); h++) {
+                            int k = tagged(parent) ? 1 : 0;
+                            if (k < T.numNodes) {
+                                int bit = k * 2 + (leftFirst ? 1 : 0);
+                                if (T.tagCand[bit] >= 0) tagMask |= 1u << bit;
+                            }
                         }
                     }
                 } else {
@@ -494,6 +607,8 @@ KDPT_HD void traceRef(const Tree& T, V3 o, V3 d, float tMinIn, Hit& H, float* la
             cur = next;
         }
     }
+    // bary.x/.y of the triangle that wrote bary.z last (the reference's own x/y may come from a later triangle that
+    // failed the second test; nothing ever reads them)
     if (lastBary) { lastBary[0] = bu; lastBary[1] = bv; lastBary[2] = bz; }
 }
 

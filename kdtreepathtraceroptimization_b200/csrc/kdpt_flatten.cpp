@@ -1,15 +1,20 @@
 // kdpt_flatten.cpp — see kdpt_flatten.h.
 #include "kdpt_flatten.h"
 #include <string.h>
+#include <algorithm>
+#include <math.h>
 #include <unordered_map>
 
 namespace kdpt {
+
+static const int kChunkMinLeaf = 128;   // leaves at least this large get 32-triangle chunks with bounding boxes
 
 uint64_t FlatTree::bytes() const
 {
     return nodes.size() * sizeof(HostNode) + (boxLo.size() + boxHi.size()) * sizeof(HostF4) +
            (triA.size() + triB.size() + nrmA.size() + nrmB.size()) * sizeof(HostF4) +
-           (triC.size() + nrmC.size()) * sizeof(HostF2);
+           (triC.size() + nrmC.size()) * sizeof(HostF2) + triOrig.size() * sizeof(int) +
+           (chunkLo.size() + chunkHi.size()) * sizeof(HostF4);
 }
 
 namespace {
@@ -90,25 +95,92 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
     out.tagCand[0] = nodes[0].leftID; out.tagCand[1] = nodes[0].rightID;
     if (numNodes > 1) { out.tagCand[2] = nodes[1].leftID; out.tagCand[3] = nodes[1].rightID; }
 
+    // canonical index = first TriBare entry holding identical 76 bytes (what kdpt_hit.tri reports)
+    std::vector<int> canon((size_t)numTris);
+    {
+        std::unordered_map<TriKey, int, TriKeyHash> first;
+        first.reserve((size_t)numTris);
+        for (int i = 0; i < numTris; i++) {
+            TriKey k; memcpy(k.w, &tris[i], sizeof k.w);
+            auto it = first.find(k);
+            if (it == first.end()) { first.emplace(k, i); canon[i] = i; } else canon[i] = it->second;
+        }
+    }
+    // Leaf-local culling structure. The reference builder stops at depth 14 or as soon as a split keeps every
+    // triangle on one side, so leaves hold hundreds to tens of thousands of triangles (986 on dragon_5, 62 080 on the
+    // 1.6 M dragon). Leaves with at least kChunkMinLeaf entries are reordered along a Morton curve of the triangle
+    // centroids and cut into chunks of 32 consecutive entries with a padded AABB each; the kernels test a ray against
+    // the chunk boxes first and only stream the chunks it can touch. A triangle is never skipped if its exact test
+    // could pass: the computed hit point lies on the triangle up to rounding (<< pad), hence inside its chunk box.
+    // The order inside a leaf is free: the exact modes break ties on the canonical index and the reference-compatible
+    // modes reconstruct the reference's sequential semantics from triOrig (see traceRef).
+    std::vector<int> order((size_t)numTris);
+    for (int i = 0; i < numTris; i++) order[i] = i;
+    float sceneMax = 0.f;
+    for (int a = 0; a < 3; a++) sceneMax = fmaxf(sceneMax, fmaxf(fabsf(out.rootLo[a]), fabsf(out.rootHi[a])));
+    const float pad = fmaxf(1e-4f, 2e-5f * sceneMax);
+    auto vert = [&](int i, int k, int a) -> float {
+        const kdpt_tri_bare& t = tris[i];
+        const float* x = &t.x1;          // x1 x2 x3 y1 y2 y3 z1 z2 z3
+        return x[3 * a + k];
+    };
+    for (int nId = 0; nId < numNodes; nId++) {
+        HostNode& h = out.nodes[nId];
+        if ((h.w & 3u) != 3u) continue;
+        h.z = 0xffffffffu;
+        const int start = (int)h.x, count = (int)h.y;
+        if (count < kChunkMinLeaf) continue;
+        // Morton order of centroids inside the leaf's own centroid bounds
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        std::vector<float> cen(3 * (size_t)count);
+        for (int j = 0; j < count; j++)
+            for (int a = 0; a < 3; a++) {
+                float c = (vert(start + j, 0, a) + vert(start + j, 1, a) + vert(start + j, 2, a)) * (1.0f / 3.0f);
+                if (!(c == c)) c = 0.f;
+                cen[3 * (size_t)j + a] = c; lo[a] = fminf(lo[a], c); hi[a] = fmaxf(hi[a], c);
+            }
+        std::vector<std::pair<uint32_t, int>> keys((size_t)count);
+        for (int j = 0; j < count; j++) {
+            uint32_t code = 0;
+            uint32_t q[3];
+            for (int a = 0; a < 3; a++) {
+                float ext = hi[a] - lo[a];
+                float f = ext > 0 ? (cen[3 * (size_t)j + a] - lo[a]) / ext : 0.f;
+                int v = (int)(f * 1023.0f); q[a] = (uint32_t)(v < 0 ? 0 : (v > 1023 ? 1023 : v));
+            }
+            for (int b = 9; b >= 0; b--) for (int a = 0; a < 3; a++) code = (code << 1) | ((q[a] >> b) & 1u);
+            keys[j] = std::make_pair(code, start + j);
+        }
+        std::sort(keys.begin(), keys.end());
+        for (int j = 0; j < count; j++) order[start + j] = keys[j].second;
+        h.z = (uint32_t)out.chunkLo.size();
+        for (int c0 = 0; c0 < count; c0 += 32) {
+            float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int j = c0; j < count && j < c0 + 32; j++)
+                for (int k = 0; k < 3; k++)
+                    for (int a = 0; a < 3; a++) { float x = vert(order[start + j], k, a); blo[a] = fminf(blo[a], x); bhi[a] = fmaxf(bhi[a], x); }
+            out.chunkLo.push_back(HostF4{blo[0] - pad, blo[1] - pad, blo[2] - pad, 0.f});
+            out.chunkHi.push_back(HostF4{bhi[0] + pad, bhi[1] + pad, bhi[2] + pad, 0.f});
+        }
+    }
+    out.numChunks = (int)out.chunkLo.size();
+
     out.triA.resize(numTris); out.triB.resize(numTris); out.triC.resize(numTris);
     out.nrmA.resize(numTris); out.nrmB.resize(numTris); out.nrmC.resize(numTris);
-    std::unordered_map<TriKey, int, TriKeyHash> first;
-    first.reserve((size_t)numTris);
+    out.triOrig.resize(numTris);
     for (int i = 0; i < numTris; i++) {
-        const kdpt_tri_bare& t = tris[i];
-        TriKey k; memcpy(k.w, &t, sizeof k.w);
-        auto it = first.find(k);
-        int canon = i;
-        if (it == first.end()) first.emplace(k, i); else canon = it->second;
+        const int src = order[i];
+        const kdpt_tri_bare& t = tris[src];
         // e1 = v1 - v0, e2 = v2 - v0: binary32 subtractions, the same the reference performs per test
         float e1x = t.x2 - t.x1, e1y = t.y2 - t.y1, e1z = t.z2 - t.z1;
         float e2x = t.x3 - t.x1, e2y = t.y3 - t.y1, e2z = t.z3 - t.z1;
         out.triA[i] = HostF4{t.x1, t.y1, t.z1, e1x};
         out.triB[i] = HostF4{e1y, e1z, e2x, e2y};
-        out.triC[i] = HostF2{e2z, asFloat(canon)};
+        out.triC[i] = HostF2{e2z, asFloat(canon[src])};
         out.nrmA[i] = HostF4{t.nx1, t.ny1, t.nz1, t.nx2};
         out.nrmB[i] = HostF4{t.ny2, t.nz2, t.nx3, t.ny3};
         out.nrmC[i] = HostF2{t.nz3, asFloat(t.mtlIdx)};
+        out.triOrig[i] = src;
     }
     return true;
 }

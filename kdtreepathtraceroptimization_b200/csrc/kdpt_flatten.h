@@ -17,10 +17,12 @@ struct FlatTree {
     std::vector<HostF4> boxLo, boxHi;
     std::vector<HostF4> triA, triB, nrmA, nrmB;
     std::vector<HostF2> triC, nrmC;
+    std::vector<int> triOrig;                   // TriBare index of every (possibly reordered) leaf entry
+    std::vector<HostF4> chunkLo, chunkHi;       // padded AABB of every 32-triangle chunk of the chunked leaves
+    int numChunks = 0;
     float rootLo[3] = {0, 0, 0}, rootHi[3] = {0, 0, 0};
     int tagCand[4] = {-1, -1, -1, -1};
     int numNodes = 0, numTris = 0, maxDepth = 0, maxLeaf = 0;
-    // level-order ("top of tree") staging list for shared memory: node indices with depth < topLevels
     uint64_t bytes() const;
 };
 
