@@ -180,6 +180,8 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     if ((rc = upload(ctx->treeMem[9], flat.triOrig, &T.triOrig, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[10], flat.chunkLo, (const HostF4**)&T.chunkLo, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[11], flat.chunkHi, (const HostF4**)&T.chunkHi, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[12], flat.superLo, (const HostF4**)&T.superLo, s))) return fail(rc);
+    if ((rc = upload(ctx->treeMem[13], flat.superHi, (const HostF4**)&T.superHi, s))) return fail(rc);
     T.numNodes = flat.numNodes; T.numTris = flat.numTris;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = flat.rootLo[a]; T.rootHi[a] = flat.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = flat.tagCand[k];
@@ -209,6 +211,7 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     flat.nrmA.clear(); flat.nrmA.shrink_to_fit(); flat.nrmB.clear(); flat.nrmB.shrink_to_fit();
     flat.nrmC.clear(); flat.nrmC.shrink_to_fit(); flat.triOrig.clear(); flat.triOrig.shrink_to_fit();
     flat.chunkLo.clear(); flat.chunkLo.shrink_to_fit(); flat.chunkHi.clear(); flat.chunkHi.shrink_to_fit();
+    flat.superLo.clear(); flat.superLo.shrink_to_fit(); flat.superHi.clear(); flat.superHi.shrink_to_fit();
     ctx->info = flat;
     *out = ctx;
     return KDPT_OK;

@@ -61,6 +61,8 @@ struct Tree {
     const int* triOrig;      // TriBare index of entry i (entries of chunked leaves are Morton-reordered)
     const float4* chunkLo;   // padded AABBs of the 32-entry chunks of chunked leaves (leaf record .z = first chunk)
     const float4* chunkHi;
+    const float4* superLo;   // boxes of groups of 32 chunks (leaves with >= 64 chunks); chunkLo[first].w = first group
+    const float4* superHi;
     int numNodes;
     int numTris;
     float rootLo[3], rootHi[3];
@@ -199,9 +201,9 @@ KDPT_HD bool acceptHit(const Tree& T, int i, int canon, V3 o, V3 d, float u, flo
 
 // ray (line) against the padded box of chunk c: entry / exit parameters. NaNs (0 * inf) drop out of fminf/fmaxf,
 // which only widens the interval.
-KDPT_HD void chunkInterval(const Tree& T, int c, V3 o, V3 inv, float& tn, float& tf)
+KDPT_HD void boxInterval(const float4* los, const float4* his, int c, V3 o, V3 inv, float& tn, float& tf)
 {
-    float4 lo = KDPT_LDG(T.chunkLo + c), hi = KDPT_LDG(T.chunkHi + c);
+    float4 lo = KDPT_LDG(los + c), hi = KDPT_LDG(his + c);
     float v1 = (lo.x - o.x) * inv.x, v2 = (hi.x - o.x) * inv.x;
     float v3 = (lo.y - o.y) * inv.y, v4 = (hi.y - o.y) * inv.y;
     float v5 = (lo.z - o.z) * inv.z, v6 = (hi.z - o.z) * inv.z;
@@ -210,12 +212,20 @@ KDPT_HD void chunkInterval(const Tree& T, int c, V3 o, V3 inv, float& tn, float&
 }
 // exact modes: a chunk can be skipped when the ray misses its box, leaves it behind the origin, or enters it beyond
 // the best hit so far (zlim = best glm t + slack). Written so that any NaN keeps the chunk.
+KDPT_HD void chunkInterval(const Tree& T, int c, V3 o, V3 inv, float& tn, float& tf) { boxInterval(T.chunkLo, T.chunkHi, c, o, inv, tn, tf); }
 KDPT_HD bool chunkMayHit(const Tree& T, int c, V3 o, V3 inv, float zlim, float slack)
 {
     float tn, tf;
     chunkInterval(T, c, o, inv, tn, tf);
     return !(tn > tf) && !(tf < -slack) && !(tn > zlim);
 }
+KDPT_HD bool superMayHit(const Tree& T, int g, V3 o, V3 inv, float zlim, float slack)
+{
+    float tn, tf;
+    boxInterval(T.superLo, T.superHi, g, o, inv, tn, tf);
+    return !(tn > tf) && !(tf < -slack) && !(tn > zlim);
+}
+KDPT_HD int superFirst(const Tree& T, unsigned chunk0) { return __float_as_int(KDPT_LDG(T.chunkLo + chunk0).w); }
 
 KDPT_HD void initHit(Hit& H, float tMinIn)
 {
@@ -290,10 +300,12 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
         if (count > 0) {
             if (COUNT) ctr->leaves++;
             const int nch = nd.z != kNoChunks ? (count + 31) >> 5 : 1;
+            const int sup0 = nd.z != kNoChunks ? superFirst(T, nd.z) : -1;
             for (int c = 0; c < nch; c++) {
                 int b = start, e = start + count;
                 if (nd.z != kNoChunks) {
                     float zl = (H.tri >= 0 ? fminf(H.z, zbound) : zbound) + slack;
+                    if (sup0 >= 0 && (c & 31) == 0 && !superMayHit(T, sup0 + (c >> 5), o, inv, zl, slack)) { c += 31; continue; }
                     if (!chunkMayHit(T, (int)nd.z + c, o, inv, zl, slack)) continue;
                     b = start + 32 * c; e = b + 32 < start + count ? b + 32 : start + count;
                 }
@@ -431,10 +443,11 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
             float zlim = __shfl_sync(FULL, (H.tri >= 0 ? fminf(H.z, zbound) : zbound) + slack, src);
             Hit L; L.t = bestT; L.tri = bestTri; L.z = FLT_MAX; L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
             const int nch = (ccount + 31) >> 5;
-            for (int cb = 0; cb < nch; cb += 32) {
+            // 32 chunk boxes per step; the chunks the ray can touch are then streamed one per step
+            auto chunkGroup = [&](int cb) {
                 const int c = cb + (int)lane;
                 unsigned hitMask = __ballot_sync(FULL, c < nch && chunkMayHit(T, cchunk0 + c, O, INV, zlim, cslack));
-                if (!hitMask) continue;
+                if (!hitMask) return;
                 while (hitMask) {
                     const int j = __ffs(hitMask) - 1;
                     hitMask &= hitMask - 1;
@@ -446,11 +459,27 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                     }
                 }
                 // tighten the cull distance with whatever any lane has found so far (only worth it on long leaves)
-                if (cb + 32 < nch) {
+                if (nch > 32) {
                     float lz = (L.t != bestT || L.tri != bestTri) ? L.z : FLT_MAX;
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) lz = fminf(lz, __shfl_xor_sync(FULL, lz, off));
                     if (lz < FLT_MAX) zlim = fminf(zlim, lz + cslack);
+                }
+            };
+            const int sup0 = superFirst(T, (unsigned)cchunk0);
+            if (sup0 < 0) {
+                for (int cb = 0; cb < nch; cb += 32) chunkGroup(cb);
+            } else {
+                // very fat leaf: 32 group boxes (32 x 32 x 32 triangles) per step first
+                const int nsup = (nch + 31) >> 5;
+                for (int sb = 0; sb < nsup; sb += 32) {
+                    const int g = sb + (int)lane;
+                    unsigned gm = __ballot_sync(FULL, g < nsup && superMayHit(T, sup0 + g, O, INV, zlim, cslack));
+                    while (gm) {
+                        const int j = __ffs(gm) - 1;
+                        gm &= gm - 1;
+                        chunkGroup((sb + j) * 32);
+                    }
                 }
             }
             reduceToOwner(src, bestT, bestTri, L);
@@ -555,10 +584,15 @@ KDPT_HD void traceRef(const Tree& T, V3 o, V3 d, float tMinIn, Hit& H, float* la
                     int zOrig = -1, mtlOrig = -1, accOrig = -1, nHits = 0;
                     float zNew = bz;
                     const int nch = nd.z != kNoChunks ? (count + 31) >> 5 : 1;
+                    const int sup0 = nd.z != kNoChunks ? superFirst(T, nd.z) : -1;
                     for (int c = 0; c < nch; c++) {
                         int b = start, e = start + count;
                         if (nd.z != kNoChunks) {
                             float tn, tf;
+                            if (sup0 >= 0 && (c & 31) == 0) {
+                                boxInterval(T.superLo, T.superHi, sup0 + (c >> 5), o, inv, tn, tf);
+                                if (tn > tf) { c += 31; continue; }
+                            }
                             chunkInterval(T, (int)nd.z + c, o, inv, tn, tf);
                             if (tn > tf) continue;
                             b = start + 32 * c; e = b + 32 < start + count ? b + 32 : start + count;

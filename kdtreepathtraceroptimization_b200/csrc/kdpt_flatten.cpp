@@ -7,14 +7,15 @@
 
 namespace kdpt {
 
-static const int kChunkMinLeaf = 128;   // leaves at least this large get 32-triangle chunks with bounding boxes
+static const int kChunkMinLeaf = 128;
+static const int kSuperMinChunks = 64;   // leaves with at least this many chunks (2048 triangles) get a second level   // leaves at least this large get 32-triangle chunks with bounding boxes
 
 uint64_t FlatTree::bytes() const
 {
     return nodes.size() * sizeof(HostNode) + (boxLo.size() + boxHi.size()) * sizeof(HostF4) +
            (triA.size() + triB.size() + nrmA.size() + nrmB.size()) * sizeof(HostF4) +
            (triC.size() + nrmC.size()) * sizeof(HostF2) + triOrig.size() * sizeof(int) +
-           (chunkLo.size() + chunkHi.size()) * sizeof(HostF4);
+           (chunkLo.size() + chunkHi.size() + superLo.size() + superHi.size()) * sizeof(HostF4);
 }
 
 namespace {
@@ -154,13 +155,30 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
         std::sort(keys.begin(), keys.end());
         for (int j = 0; j < count; j++) order[start + j] = keys[j].second;
         h.z = (uint32_t)out.chunkLo.size();
+        const size_t firstChunk = out.chunkLo.size();
         for (int c0 = 0; c0 < count; c0 += 32) {
             float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
             for (int j = c0; j < count && j < c0 + 32; j++)
                 for (int k = 0; k < 3; k++)
                     for (int a = 0; a < 3; a++) { float x = vert(order[start + j], k, a); blo[a] = fminf(blo[a], x); bhi[a] = fmaxf(bhi[a], x); }
-            out.chunkLo.push_back(HostF4{blo[0] - pad, blo[1] - pad, blo[2] - pad, 0.f});
+            out.chunkLo.push_back(HostF4{blo[0] - pad, blo[1] - pad, blo[2] - pad, asFloat(-1)});
             out.chunkHi.push_back(HostF4{bhi[0] + pad, bhi[1] + pad, bhi[2] + pad, 0.f});
+        }
+        // second level for very fat leaves: one box per 32 consecutive chunks (1024 triangles); the first chunk's
+        // lo.w carries the index of the leaf's first super box (-1: none)
+        const size_t nch = out.chunkLo.size() - firstChunk;
+        if ((int)nch >= kSuperMinChunks) {
+            out.chunkLo[firstChunk].w = asFloat((int)out.superLo.size());
+            for (size_t g = 0; g < nch; g += 32) {
+                float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+                for (size_t c = g; c < nch && c < g + 32; c++) {
+                    const HostF4& l = out.chunkLo[firstChunk + c]; const HostF4& u = out.chunkHi[firstChunk + c];
+                    blo[0] = fminf(blo[0], l.x); blo[1] = fminf(blo[1], l.y); blo[2] = fminf(blo[2], l.z);
+                    bhi[0] = fmaxf(bhi[0], u.x); bhi[1] = fmaxf(bhi[1], u.y); bhi[2] = fmaxf(bhi[2], u.z);
+                }
+                out.superLo.push_back(HostF4{blo[0], blo[1], blo[2], 0.f});
+                out.superHi.push_back(HostF4{bhi[0], bhi[1], bhi[2], 0.f});
+            }
         }
     }
     out.numChunks = (int)out.chunkLo.size();

@@ -19,6 +19,7 @@ struct FlatTree {
     std::vector<HostF2> triC, nrmC;
     std::vector<int> triOrig;                   // TriBare index of every (possibly reordered) leaf entry
     std::vector<HostF4> chunkLo, chunkHi;       // padded AABB of every 32-triangle chunk of the chunked leaves
+    std::vector<HostF4> superLo, superHi;       // AABB of every group of 32 chunks of the very fat leaves
     int numChunks = 0;
     float rootLo[3] = {0, 0, 0}, rootHi[3] = {0, 0, 0};
     int tagCand[4] = {-1, -1, -1, -1};

@@ -43,7 +43,7 @@ struct kdpt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     kdpt::Tree tree{};                 // device pointers
-    kdpt::DeviceBuffer treeMem[12];
+    kdpt::DeviceBuffer treeMem[14];
     kdpt::FlatTree info;               // host copy of the sizes only (vectors released after upload)
     uint64_t deviceBytes = 0;
     kdpt::SceneDev scene;
