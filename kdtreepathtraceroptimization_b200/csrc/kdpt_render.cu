@@ -44,6 +44,7 @@ struct IterConst {
 };
 
 constexpr int kMaxBatch = 16;           // iterations (samples) processed together by every launch
+constexpr int kTicketPackets = 1;       // 32-path packets a warp takes per ticket (amortises the atomic + segment lookup)
 
 struct LoopState {
     int np[kMaxBatch][kMaxBounces + 2];      // live paths of each batched iteration at the start of each bounce
@@ -59,12 +60,13 @@ struct Batch {
 };
 struct IterConsts { IterConst c[kMaxBatch]; };
 
-// flat packet ticket -> (segment, first path of the packet); pk[] = exclusive prefix of packets per segment (smem)
-__device__ __forceinline__ void buildPacketPrefix(int* pk, const LoopState* st, int B, int depth)
+// flat ticket -> (segment, first packet); pk[] = exclusive prefix of tickets per segment (smem); a ticket is
+// `per` consecutive 32-path packets of one segment
+__device__ __forceinline__ void buildPacketPrefix(int* pk, const LoopState* st, int B, int depth, int per)
 {
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int s = 0; s < B; s++) { pk[s] = acc; acc += (st->np[s][depth] + 31) >> 5; }
+        for (int s = 0; s < B; s++) { pk[s] = acc; acc += (((st->np[s][depth] + 31) >> 5) + per - 1) / per; }
         pk[B] = acc;
     }
     __syncthreads();
@@ -189,7 +191,7 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         unsigned* dst = reinterpret_cast<unsigned*>(sGeoms);
         for (int k = threadIdx.x; k < ng * (int)(sizeof(kdpt_geom) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
     }
-    buildPacketPrefix(pk, st, bt.B, A.depth);
+    buildPacketPrefix(pk, st, bt.B, A.depth, kTicketPackets);
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long liveLocal = 0;
     for (;;) {
@@ -199,9 +201,13 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         if (ticket >= pk[bt.B]) break;
         const int seg = findSegment(pk, bt.B, ticket);
         const int n = st->np[seg][A.depth];
-        const unsigned i = (unsigned)(ticket - pk[seg]) * 32u + lane;      // path index inside its iteration
-        const size_t slot = (size_t)seg * bt.cap + i;
         const int iter = bt.iterBase + seg * bt.iterStride;
+        const int numPackets = (n + 31) >> 5;
+      for (int q = 0; q < kTicketPackets; q++) {
+        const int packet = (ticket - pk[seg]) * kTicketPackets + q;
+        if (packet >= numPackets) break;
+        const unsigned i = (unsigned)packet * 32u + lane;                  // path index inside its iteration
+        const size_t slot = (size_t)seg * bt.cap + i;
         bool alive = false, live = false;
         // ---- phase A (per lane): load the path, test the analytic geoms ----
         int2 bm = make_int2(0, 0);
@@ -209,10 +215,9 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         PathRay r; r.o = mk(0, 0, 0); r.d = mk(0, 0, 0); r.inside = false; r.sdepth = 0.f;
         float tMin = FLT_MAX; int hitGeom = -1; V3 ipoint = mk(0, 0, 0), normal = mk(0, 0, 0);
         if (i < (unsigned)n) {
-            bm = P.bm[slot];
+            bm = P.bm[slot]; od = P.od[slot]; dr = P.dr[slot]; cp = P.cp[slot];     // four independent loads, one round trip
             if (bm.x > 0) {
                 live = true;
-                od = P.od[slot]; dr = P.dr[slot]; cp = P.cp[slot];
                 r.o = mk(od.x, od.y, od.z); r.d = mk(dr.x, dr.y, dr.z); r.inside = dr.w != 0.0f; r.sdepth = od.w;
             }
         }
@@ -286,9 +291,10 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
         unsigned liveMask = __ballot_sync(0xffffffffu, live);
         if (lane == 0) {
-            if (packetCount) packetCount[seg * bt.capPackets + (ticket - pk[seg])] = __popc(aliveMask);
+            if (packetCount) packetCount[seg * bt.capPackets + packet] = __popc(aliveMask);
             liveLocal += (unsigned)__popc(liveMask);
         }
+      }
     }
     if (lane == 0 && liveLocal && A.depth < kMaxBounces) atomicAdd(&st->bounceRays[A.depth], liveLocal);
 }
@@ -335,26 +341,22 @@ scanPacketsKernel(int* __restrict__ packetCountAll, LoopState* st, int depth, in
 __global__ void __launch_bounds__(kThreads)
 compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset, LoopState* st, int depth, Batch bt)
 {
-    __shared__ int pk[kMaxBatch + 1];
-    buildPacketPrefix(pk, st, bt.B, depth);
     const unsigned lane = threadIdx.x & 31u;
-    for (;;) {
-        int ticket = 0;
-        if (lane == 0) ticket = (int)atomicAdd(&st->ticket[9 + depth], 1u);
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket >= pk[bt.B]) break;
-        const int seg = findSegment(pk, bt.B, ticket);
+    const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, numWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int seg = 0; seg < bt.B; seg++) {
         const int n = st->np[seg][depth];
-        const int packet = ticket - pk[seg];
-        const unsigned i = (unsigned)packet * 32u + lane;
-        const size_t slot = (size_t)seg * bt.cap + i;
-        int2 bm = make_int2(0, 0);
-        if (i < (unsigned)n) bm = P.bm[slot];
-        bool alive = i < (unsigned)n && bm.x != 0;          // is_zero_bounce, pathtrace.cu:103-110
-        unsigned mask = __ballot_sync(0xffffffffu, alive);
-        if (alive) {
-            size_t dst = (size_t)seg * bt.cap + packetOffset[seg * bt.capPackets + packet] + __popc(mask & ((1u << lane) - 1u));
-            Q.od[dst] = P.od[slot]; Q.dr[dst] = P.dr[slot]; Q.cp[dst] = P.cp[slot]; Q.bm[dst] = bm;
+        const int numPackets = (n + 31) >> 5;
+        for (int packet = warpId; packet < numPackets; packet += numWarps) {      // uniform work: static striding
+            const unsigned i = (unsigned)packet * 32u + lane;
+            const size_t slot = (size_t)seg * bt.cap + i;
+            int2 bm = make_int2(0, 0);
+            if (i < (unsigned)n) bm = P.bm[slot];
+            bool alive = i < (unsigned)n && bm.x != 0;          // is_zero_bounce, pathtrace.cu:103-110
+            unsigned mask = __ballot_sync(0xffffffffu, alive);
+            if (alive) {
+                size_t dst = (size_t)seg * bt.cap + packetOffset[seg * bt.capPackets + packet] + __popc(mask & ((1u << lane) - 1u));
+                Q.od[dst] = P.od[slot]; Q.dr[dst] = P.dr[slot]; Q.cp[dst] = P.cp[slot]; Q.bm[dst] = bm;
+            }
         }
     }
 }
