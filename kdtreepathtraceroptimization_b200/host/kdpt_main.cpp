@@ -1,0 +1,163 @@
+// kdpt_render — headless driver over the C ABI (include/kdpt.h): what the reference's main.cpp does without the GLFW
+// window: `prog SCENE.txt [MESH.obj]` (main.cpp:1013-1038), first-frame camera (main.cpp:1053-1073, 1111-1129),
+// ITERATIONS calls of pathtrace() (runCuda, main.cpp:1139-1178) and saveImage() (main.cpp:1087-1108: x mirrored,
+// divided by the sample count; image.cpp:22-44: clamp to [0,1] * 255, truncated). Runtime toggles that the reference
+// flips with keys (main.cpp:35-60, 1187-1306) are command-line flags here.
+#include <kdpt.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+static void usage()
+{
+    fprintf(stderr,
+            "usage: kdpt_render SCENE.txt [MESH.obj] [options]\n"
+            "  --spp N            samples (default: ITERATIONS of the scene file)\n"
+            "  --res WxH          override RES\n"
+            "  --mode M           ref_t2 (default, = SHORTSTACK on), ref_t1, shortstack, fullstack\n"
+            "  --no-aa  --dof-angle A  --focal F  --softness S  --sss  --no-compaction  --sort 0|1|2\n"
+            "  --kd-depth D       KD build depth (default 13)   --synth-normals   --device N\n"
+            "  --out FILE         .png (8-bit, like the reference), .pfm (float radiance / spp) or .ppm\n"
+            "  --json             print one JSON line with timings\n");
+}
+
+// ---- minimal PNG writer (stored deflate blocks; no external library) ------------------------------------------------
+static uint32_t crcTable[256];
+static void crcInit() { for (uint32_t n = 0; n < 256; n++) { uint32_t c = n; for (int k = 0; k < 8; k++) c = c & 1 ? 0xedb88320u ^ (c >> 1) : c >> 1; crcTable[n] = c; } }
+static uint32_t crc(uint32_t c, const uint8_t* p, size_t n) { c = ~c; for (size_t i = 0; i < n; i++) c = crcTable[(c ^ p[i]) & 0xff] ^ (c >> 8); return ~c; }
+static void be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
+static void chunk(FILE* f, const char* tag, const std::vector<uint8_t>& data)
+{
+    std::vector<uint8_t> b; be32(b, (uint32_t)data.size());
+    fwrite(b.data(), 1, 4, f);
+    std::vector<uint8_t> td(tag, tag + 4); td.insert(td.end(), data.begin(), data.end());
+    fwrite(td.data(), 1, td.size(), f);
+    std::vector<uint8_t> c; be32(c, crc(0, td.data(), td.size()));
+    fwrite(c.data(), 1, 4, f);
+}
+static bool writePng(const char* path, const uint8_t* rgb, int w, int h)
+{
+    FILE* f = fopen(path, "wb");
+    if (!f) return false;
+    crcInit();
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    fwrite(sig, 1, 8, f);
+    std::vector<uint8_t> ihdr; be32(ihdr, w); be32(ihdr, h); ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
+    chunk(f, "IHDR", ihdr);
+    std::vector<uint8_t> raw; raw.reserve((size_t)h * (3 * w + 1));
+    for (int y = 0; y < h; y++) { raw.push_back(0); raw.insert(raw.end(), rgb + (size_t)y * 3 * w, rgb + (size_t)(y + 1) * 3 * w); }
+    std::vector<uint8_t> z; z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;
+    for (size_t off = 0; off < raw.size() || off == 0;) {
+        size_t n = raw.size() - off; if (n > 65535) n = 65535;
+        z.push_back(off + n >= raw.size() ? 1 : 0);
+        z.push_back(n & 0xff); z.push_back(n >> 8); z.push_back(~n & 0xff); z.push_back((~n >> 8) & 0xff);
+        for (size_t i = 0; i < n; i++) { a = (a + raw[off + i]) % 65521; b = (b + a) % 65521; }
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        off += n;
+        if (n == 0) break;
+    }
+    be32(z, (b << 16) | a);
+    chunk(f, "IDAT", z);
+    chunk(f, "IEND", std::vector<uint8_t>());
+    fclose(f);
+    return true;
+}
+
+static int fail(const char* what) { fprintf(stderr, "kdpt_render: %s: %s\n", what, kdpt_last_error()); return 1; }
+
+int main(int argc, char** argv)
+{
+    if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage(); return argc < 2 ? 2 : 0; }
+    std::string sceneTxt = argv[1], obj, out = "";
+    int spp = -1, resW = 0, resH = 0, kdDepth = 13, synth = 0, device = 0, json = 0;
+    kdpt_params p; memset(&p, 0, sizeof p);
+    p.focalLength = 6.0f; p.dofAngle = 0.0f; p.softness = 0.0f; p.antialias = 1; p.enableSss = 0; p.compaction = 1;
+    p.mode = KDPT_REF_T2; p.sortByMaterial = 1;                      // main.cpp:35-60
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
+        if (a == "--spp") spp = atoi(next());
+        else if (a == "--res") { if (sscanf(next(), "%dx%d", &resW, &resH) != 2) { usage(); return 2; } }
+        else if (a == "--mode") {
+            std::string m = next();
+            if (m == "ref_t2") p.mode = KDPT_REF_T2; else if (m == "ref_t1") p.mode = KDPT_REF_T1;
+            else if (m == "shortstack") p.mode = KDPT_SHORTSTACK; else if (m == "fullstack") p.mode = KDPT_FULLSTACK;
+            else { usage(); return 2; }
+        }
+        else if (a == "--no-aa") p.antialias = 0;
+        else if (a == "--dof-angle") p.dofAngle = (float)atof(next());
+        else if (a == "--focal") p.focalLength = (float)atof(next());
+        else if (a == "--softness") p.softness = (float)atof(next());
+        else if (a == "--sss") p.enableSss = 1;
+        else if (a == "--no-compaction") p.compaction = 0;
+        else if (a == "--sort") p.sortByMaterial = atoi(next());
+        else if (a == "--kd-depth") kdDepth = atoi(next());
+        else if (a == "--synth-normals") synth = 1;
+        else if (a == "--device") device = atoi(next());
+        else if (a == "--out") out = next();
+        else if (a == "--json") json = 1;
+        else if (a.size() && a[0] != '-' && obj.empty()) obj = a;
+        else { usage(); return 2; }
+    }
+    kdpt_host_scene* hs = nullptr;
+    if (kdpt_scene_load(sceneTxt.c_str(), obj.empty() ? nullptr : obj.c_str(), nullptr, kdDepth, synth, &hs)) return fail("scene");
+    kdpt_scene sc; int iterations = 0;
+    kdpt_scene_view(hs, &sc, &iterations);
+    if (resW > 0 && resH > 0) {                                       // scene.cpp:216-223 with the new RES
+        const float PI = 3.1415926535897932384626422832795028841971f;
+        float yscaled = tanf(sc.camera.fov[1] * (PI / 180));
+        float xscaled = (yscaled * resW) / resH;
+        sc.camera.resolution[0] = resW; sc.camera.resolution[1] = resH;
+        sc.camera.pixelLength[0] = 2 * xscaled / (float)resW; sc.camera.pixelLength[1] = 2 * yscaled / (float)resH;
+    }
+    kdpt_camera_first_frame(&sc.camera);
+    if (spp < 0) spp = iterations;
+    const int W = sc.camera.resolution[0], H = sc.camera.resolution[1];
+    kdpt_ctx* ctx = nullptr;
+    if (kdpt_create(&sc, device, &ctx)) return fail("create");
+    kdpt_render_stats st; memset(&st, 0, sizeof st);
+    if (kdpt_render(ctx, 1, spp, 1, &p, &st)) return fail("render");
+    std::vector<float> img((size_t)W * H * 3);
+    if (kdpt_get_image(ctx, img.data())) return fail("get_image");
+    if (!out.empty()) {
+        const float samples = (float)(spp > 0 ? spp : 1);
+        bool pfm = out.size() > 4 && out.substr(out.size() - 4) == ".pfm";
+        bool ppm = out.size() > 4 && out.substr(out.size() - 4) == ".ppm";
+        if (pfm) {
+            FILE* f = fopen(out.c_str(), "wb");
+            if (!f) { fprintf(stderr, "kdpt_render: cannot write %s\n", out.c_str()); return 1; }
+            fprintf(f, "PF\n%d %d\n-1.0\n", W, H);
+            for (int y = H - 1; y >= 0; y--)
+                for (int x = 0; x < W; x++) { float px[3]; for (int c = 0; c < 3; c++) px[c] = img[3 * ((size_t)y * W + (W - 1 - x)) + c] / samples; fwrite(px, 4, 3, f); }
+            fclose(f);
+        } else {
+            std::vector<uint8_t> rgb((size_t)W * H * 3);
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++)
+                    for (int c = 0; c < 3; c++) {
+                        float v = img[3 * ((size_t)y * W + x) + c] / samples;           // main.cpp:1092-1097: setPixel(W-1-x, y, pix/samples)
+                        v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+                        rgb[3 * ((size_t)y * W + (W - 1 - x)) + c] = (uint8_t)(v * 255.f);
+                    }
+            if (ppm) {
+                FILE* f = fopen(out.c_str(), "wb");
+                if (!f) { fprintf(stderr, "kdpt_render: cannot write %s\n", out.c_str()); return 1; }
+                fprintf(f, "P6\n%d %d\n255\n", W, H); fwrite(rgb.data(), 1, rgb.size(), f); fclose(f);
+            } else if (!writePng(out.c_str(), rgb.data(), W, H)) { fprintf(stderr, "kdpt_render: cannot write %s\n", out.c_str()); return 1; }
+        }
+    }
+    if (json)
+        printf("{\"scene\": \"%s\", \"mesh\": \"%s\", \"resolution\": [%d, %d], \"spp\": %d, \"ray_bounces\": %llu, \"ms\": %.3f, "
+               "\"mrays_per_s\": %.2f, \"spp_per_s\": %.2f, \"launches\": %llu}\n",
+               sceneTxt.c_str(), obj.c_str(), W, H, spp, (unsigned long long)st.rayBounces, st.totalMs,
+               st.totalMs > 0 ? st.rayBounces / (st.totalMs * 1e3) : 0.0, st.totalMs > 0 ? spp / (st.totalMs * 1e-3) : 0.0,
+               (unsigned long long)st.launches);
+    kdpt_destroy(ctx);
+    kdpt_scene_free(hs);
+    return 0;
+}

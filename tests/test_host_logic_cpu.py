@@ -138,3 +138,16 @@ def test_product_never_touches_the_oracle():
                 assert not pat.search(txt), os.path.join(dp, f)
     out = subprocess.check_output(["nm", "-D", kdpt.LIB_PATH]).decode()
     assert "ko_" not in out and "kdref_" not in out
+
+
+def test_headless_cli_builds_and_fails_loudly_without_a_gpu():
+    import torch
+    exe = os.path.join(ROOT, "kdtreepathtraceroptimization_b200", "kdpt_render")
+    assert os.path.exists(exe)
+    assert subprocess.run([exe, "--help"], capture_output=True).returncode == 0
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    scenes = os.path.join(ROOT, "tests", "golden", "scenes")
+    r = subprocess.run([exe, os.path.join(scenes, "cornell.txt"), os.path.join(scenes, "sphere_low_1.obj"), "--spp", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr

@@ -171,3 +171,34 @@ def test_sample_sharding_is_a_partition():
         c.render(2, 3, 2, p)
         full, parts = a.image(), b.image() + c.image()
     assert np.allclose(full, parts, rtol=1e-5, atol=1e-6)
+
+
+def test_headless_cli_matches_the_library(tmp_path):
+    """kdpt_render (C++ driver over the C ABI: scene .txt + .obj -> first-frame camera -> spp iterations -> saveImage
+    semantics: x mirrored, / samples, clamp*255 truncated) writes the same pixels as the Python mirror computes"""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "kdtreepathtraceroptimization_b200", "kdpt_render")
+    scenes = os.path.join(GOLDEN, "scenes")
+    out = tmp_path / "bunny.ppm"
+    r = subprocess.run([exe, os.path.join(scenes, "cornell8.txt"), os.path.join(scenes, "stanford_bunny.obj"), "--spp", "6",
+                        "--res", "96x64", "--mode", "fullstack", "--out", str(out), "--json"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import json
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["spp"] == 6 and info["ray_bounces"] > 96 * 64 * 6
+    data = out.read_bytes()
+    hdr = b"P6\n96 64\n255\n"
+    assert data.startswith(hdr)
+    got = np.frombuffer(data[len(hdr):], np.uint8).reshape(64, 96, 3)
+    sc = kdpt.Scene.load(os.path.join(scenes, "cornell8.txt"), os.path.join(scenes, "stanford_bunny.obj")).with_resolution(96, 64).first_frame_camera()
+    with kdpt.Context(sc) as ctx:
+        ctx.clear_image()
+        ctx.render(1, 6, 1, kdpt.default_params(mode=kdpt.FULLSTACK))
+        img = ctx.image()
+    want = (np.clip(img / np.float32(6), 0, 1) * np.float32(255)).astype(np.uint8)[:, ::-1, :]
+    assert (got == want).all()
+    png = tmp_path / "bunny.png"
+    r = subprocess.run([exe, os.path.join(scenes, "cornell8.txt"), os.path.join(scenes, "stanford_bunny.obj"), "--spp", "1",
+                        "--res", "32x32", "--out", str(png)], capture_output=True, text=True)
+    assert r.returncode == 0 and png.read_bytes()[:8] == b"\\x89PNG\\r\\n\\x1a\\n"
