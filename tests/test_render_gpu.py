@@ -201,4 +201,4 @@ def test_headless_cli_matches_the_library(tmp_path):
     png = tmp_path / "bunny.png"
     r = subprocess.run([exe, os.path.join(scenes, "cornell8.txt"), os.path.join(scenes, "stanford_bunny.obj"), "--spp", "1",
                         "--res", "32x32", "--out", str(png)], capture_output=True, text=True)
-    assert r.returncode == 0 and png.read_bytes()[:8] == b"\\x89PNG\\r\\n\\x1a\\n"
+    assert r.returncode == 0 and png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
