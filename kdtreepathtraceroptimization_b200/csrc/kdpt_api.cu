@@ -3,6 +3,7 @@
 #include "kdpt_internal.h"
 #include <string.h>
 #include <stdlib.h>
+#include <math.h>
 
 namespace kdpt {
 
@@ -119,7 +120,7 @@ int kdpt_destroy(kdpt_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->eventPool) cudaEventDestroy(e);
     for (auto& b : ctx->treeMem) b.release();
-    DeviceBuffer* bufs[] = {&ctx->scene.geoms, &ctx->scene.materials, &ctx->scene.offsets, &ctx->rays, &ctx->tmin,
+    DeviceBuffer* bufs[] = {&ctx->scene.geoms, &ctx->scene.materials, &ctx->scene.offsets, &ctx->scene.geomBounds, &ctx->rays, &ctx->tmin,
                             &ctx->hits, &ctx->counter, &ctx->image, &ctx->pathsA, &ctx->pathsB, &ctx->isects,
                             &ctx->scanTmp, &ctx->keysTmp, &ctx->hist, &ctx->accum};
     for (auto* b : bufs) b->release();
@@ -200,6 +201,27 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     if (S.numGeoms && (e = cudaMemcpyAsync(S.geoms.p, scene->geoms, sizeof(kdpt_geom) * (size_t)S.numGeoms, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload geoms"));
     if (S.numMaterials && (e = cudaMemcpyAsync(S.materials.p, scene->materials, sizeof(kdpt_material) * (size_t)S.numMaterials, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload materials"));
     if (S.numShapes && (e = cudaMemcpyAsync(S.offsets.p, scene->objMaterialOffsets, sizeof(int) * (size_t)S.numShapes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload offsets"));
+    {
+        // World-space bounding sphere of every analytic geom (unit cube / radius-0.5 sphere under `transform`), inflated:
+        // a ray whose line passes farther than the radius from the centre provably misses the geom, so the kernel can
+        // skip the exact (and expensive) object-space test without changing any result.
+        std::vector<float> gb(4 * (size_t)(S.numGeoms > 0 ? S.numGeoms : 1), 0.f);
+        for (int g = 0; g < S.numGeoms; g++) {
+            const float* m = scene->geoms[g].transform;
+            double c0 = sqrt((double)m[0] * m[0] + (double)m[1] * m[1] + (double)m[2] * m[2]);
+            double c1 = sqrt((double)m[4] * m[4] + (double)m[5] * m[5] + (double)m[6] * m[6]);
+            double c2 = sqrt((double)m[8] * m[8] + (double)m[9] * m[9] + (double)m[10] * m[10]);
+            double r = scene->geoms[g].type == 1 ? 0.5 * (c0 + c1 + c2) : 0.5 * sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+            double cmax = fabs((double)m[12]) > fabs((double)m[13]) ? fabs((double)m[12]) : fabs((double)m[13]);
+            if (fabs((double)m[14]) > cmax) cmax = fabs((double)m[14]);
+            r = r * 1.001 + 1e-3 + 1e-5 * cmax;
+            if (!(r == r) || !(r < 1e30)) r = INFINITY;     // degenerate transform: never cull
+            gb[4 * g] = m[12]; gb[4 * g + 1] = m[13]; gb[4 * g + 2] = m[14]; gb[4 * g + 3] = (float)r;
+        }
+        if ((rc = S.geomBounds.alloc(sizeof(float) * gb.size()))) return fail(rc);
+        if ((e = cudaMemcpyAsync(S.geomBounds.p, gb.data(), sizeof(float) * gb.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload geom bounds"));
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(cudaFail(e, "cudaStreamSynchronize"));
+    }
     S.camera = scene->camera; S.traceDepth = scene->traceDepth;
     S.hasCamera = scene->camera.resolution[0] > 0 && scene->camera.resolution[1] > 0;
     if ((rc = ctx->counter.alloc(256))) return fail(rc);

@@ -28,7 +28,7 @@ struct DeviceBuffer {
 
 // device copies of the analytic scene (render loop)
 struct SceneDev {
-    DeviceBuffer geoms, materials, offsets;
+    DeviceBuffer geoms, materials, offsets, geomBounds;   // geomBounds: float4 (centre, radius) per geom
     int numGeoms = 0, numMaterials = 0, numShapes = 0;
     kdpt_camera camera{};
     int traceDepth = 0;

@@ -80,6 +80,7 @@ __device__ __forceinline__ int findSegment(const int* pk, int B, int t)
 
 struct SceneView {
     const kdpt_geom* geoms; int numGeoms;
+    const float4* geomBounds;
     const kdpt_material* materials; int numMaterials;
 };
 
@@ -184,12 +185,14 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
              int* __restrict__ packetCount, kdpt_intersection* __restrict__ isectOut)
 {
     __shared__ kdpt_geom sGeoms[kMaxSmemGeoms];
+    __shared__ float4 sBounds[kMaxSmemGeoms];
     __shared__ int pk[kMaxBatch + 1];
     const int ng = S.numGeoms < kMaxSmemGeoms ? S.numGeoms : kMaxSmemGeoms;
     {
         const unsigned* src = reinterpret_cast<const unsigned*>(S.geoms);
         unsigned* dst = reinterpret_cast<unsigned*>(sGeoms);
         for (int k = threadIdx.x; k < ng * (int)(sizeof(kdpt_geom) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
+        for (int k = threadIdx.x; k < ng; k += blockDim.x) sBounds[k] = __ldg(S.geomBounds + k);
     }
     buildPacketPrefix(pk, st, bt.B, A.depth, kTicketPackets);
     const unsigned lane = threadIdx.x & 31u;
@@ -223,7 +226,16 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         }
         const bool doIsect = live && (A.stages & KDPT_STAGE_INTERSECT);
         if (doIsect) {
+            const float dd = dot(r.d, r.d);
             for (int g = 0; g < S.numGeoms; g++) {
+                // bounding-sphere filter (see kdpt_create): skip geoms the ray provably misses, that lie behind the
+                // origin, or whose nearest point is beyond the closest hit so far. The reference's result is the
+                // minimum over geoms of a distance that is -1 for exactly those, so nothing changes. NaN -> no skip.
+                const float4 bs = g < ng ? sBounds[g] : __ldg(S.geomBounds + g);
+                const V3 oc = mk(bs.x - r.o.x, bs.y - r.o.y, bs.z - r.o.z);
+                const float oc2 = dot(oc, oc), b = dot(oc, r.d), r2 = bs.w * bs.w;
+                if (oc2 > r2 && (b < 0.0f || oc2 * dd - b * b > r2 * dd * 1.0001f)) continue;
+                if (oc2 > r2 && tMin < FLT_MAX) { float nearest = sqrtf(oc2) - bs.w; if (nearest > tMin * 1.0001f + 1e-3f) continue; }
                 V3 pt, nr;
                 float tg = g < ng ? geomTest(sGeoms[g], r.o, r.d, pt, nr) : geomTest(S.geoms[g], r.o, r.d, pt, nr);
                 if (tg > 0.0f && tMin > tg) { tMin = tg; hitGeom = g; ipoint = pt; normal = nr; }
@@ -557,7 +569,7 @@ static int checkParams(const kdpt_params* p)
 static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers& rb, PathSoA P, const Batch& bt, int depth,
                         int stages, kdpt_intersection* dIsects, uint64_t& launches)
 {
-    SceneView S{ctx->scene.geoms.as<kdpt_geom>(), ctx->scene.numGeoms, ctx->scene.materials.as<kdpt_material>(), ctx->scene.numMaterials};
+    SceneView S{ctx->scene.geoms.as<kdpt_geom>(), ctx->scene.numGeoms, ctx->scene.geomBounds.as<float4>(), ctx->scene.materials.as<kdpt_material>(), ctx->scene.numMaterials};
     BounceArgs A; A.iter = bt.iterBase; A.depth = depth; A.stages = stages; A.softness = p.softness; A.enableSss = p.enableSss;
     A.eps = (p.mode == KDPT_SHORTSTACK || p.mode == KDPT_REF_T2) ? 0.0001f : 0.00001f;
     int grid = ctx->numSMs * 8;
