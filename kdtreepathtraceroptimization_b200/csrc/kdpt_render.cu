@@ -138,23 +138,15 @@ static IterConst makeIterConst(int iter, const kdpt_params& p)
 }
 
 // ---- generateRayFromCamera ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-generateRaysKernel(kdpt_camera cam, IterConsts ics, Batch bt, int traceDepth, float focal, PathSoA P, LoopState* st,
-                   float* __restrict__ accum)
+// per-pixel part of generateRayFromCamera (pathtrace.cu:320-393) given the iteration's jitter constants
+__device__ __forceinline__ void primaryRay(const kdpt_camera& cam, const IterConst& ic, int index, float focal, V3& org, V3& dir)
 {
-    const int n = bt.npix;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0) for (int k = 0; k < 2 * (kMaxBounces + 1); k++) st->ticket[k] = 0;
-    if (g < bt.B) st->np[g][0] = n;
-    if (g >= bt.B * n) return;
-    const int seg = g / n, index = g - seg * n;
-    const IterConst& ic = ics.c[seg];
     int W = cam.resolution[0], H = cam.resolution[1];
     int x = index % W, y = index / W;
     V3 view = mk(cam.view[0], cam.view[1], cam.view[2]), right = mk(cam.right[0], cam.right[1], cam.right[2]);
     V3 up = mk(cam.up[0], cam.up[1], cam.up[2]), pos = mk(cam.position[0], cam.position[1], cam.position[2]);
-    V3 dir = normalize((view - (right * cam.pixelLength[0]) * ((float)x - (float)W * 0.5f)) -
-                       (up * cam.pixelLength[1]) * ((float)y - (float)H * 0.5f));
+    dir = normalize((view - (right * cam.pixelLength[0]) * ((float)x - (float)W * 0.5f)) -
+                    (up * cam.pixelLength[1]) * ((float)y - (float)H * 0.5f));
     if (ic.antialias) {
         dir = dir + mk(ic.jx, ic.jy, ic.jz) * 0.002f;
         dir = normalize(dir);
@@ -162,27 +154,49 @@ generateRaysKernel(kdpt_camera cam, IterConsts ics, Batch bt, int traceDepth, fl
     V3 qv = mk(ic.qx, ic.qy, ic.qz);
     V3 uv = cross(qv, dir), uuv = cross(qv, uv);
     V3 rot = dir + ((uv * ic.qw) + uuv) * 2.0f;
-    V3 org = (pos + dir * focal) - rot * focal;
+    org = (pos + dir * focal) - rot * focal;
     dir = normalize(rot);
+}
+
+// stand-alone ray generation (kdpt_generate_rays); the render loop generates the rays inside the first bounce kernel
+__global__ void __launch_bounds__(256)
+generateRaysKernel(kdpt_camera cam, IterConsts ics, Batch bt, int traceDepth, float focal, PathSoA P, LoopState* st)
+{
+    const int n = bt.npix;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) for (int k = 0; k < 2 * (kMaxBounces + 1); k++) st->ticket[k] = 0;
+    if (g < bt.B) st->np[g][0] = n;
+    if (g >= bt.B * n) return;
+    const int seg = g / n, index = g - seg * n;
+    V3 org, dir;
+    primaryRay(cam, ics.c[seg], index, focal, org, dir);
     const size_t slot = (size_t)seg * bt.cap + index;
     P.od[slot] = make_float4(org.x, org.y, org.z, 0.0f);
     P.dr[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
     P.cp[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(index));
     P.bm[slot] = make_int2(traceDepth, 0);
-    if (accum) {        // this iteration's contribution to the pixel; every pixel's path writes it at most once
-        float* a = accum + 3 * ((size_t)seg * n + index);
-        a[0] = 0.f; a[1] = 0.f; a[2] = 0.f;
-    }
 }
+
+// start of a batch: every iteration begins with one path per pixel; packet counters to zero
+__global__ void beginBatchKernel(LoopState* st, int B, int npix)
+{
+    const int g = threadIdx.x;
+    if (g < 2 * (kMaxBounces + 1)) st->ticket[g] = 0;
+    if (g < B) st->np[g][0] = npix;
+}
+
+// what the first bounce needs to make its own primary rays
+struct GenArgs { kdpt_camera cam; IterConsts ics; int traceDepth; float focal; };
 
 // ---- one bounce: intersect (+scatter) + shade + gather, persistent warps pulling 32-path packets ------------------
 #ifndef KDPT_BOUNCE_MIN_BLOCKS
 #define KDPT_BOUNCE_MIN_BLOCKS 4
 #endif
-template <int MODE>
+template <int MODE, bool GEN>
 __global__ void __launch_bounds__(kThreads, KDPT_BOUNCE_MIN_BLOCKS)
 bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch bt, float* __restrict__ accum,
-             int* __restrict__ packetCount, kdpt_intersection* __restrict__ isectOut)
+             int* __restrict__ packetCount, unsigned* __restrict__ packetAlive, kdpt_intersection* __restrict__ isectOut,
+             const GenArgs gen)
 {
     __shared__ kdpt_geom sGeoms[kMaxSmemGeoms];
     __shared__ float4 sBounds[kMaxSmemGeoms];
@@ -197,12 +211,14 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
     buildPacketPrefix(pk, st, bt.B, A.depth, kTicketPackets);
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long liveLocal = 0;
+    int segHint = 0;
     for (;;) {
         int ticket = 0;
         if (lane == 0) ticket = (int)atomicAdd(&st->ticket[A.depth], 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= pk[bt.B]) break;
-        const int seg = findSegment(pk, bt.B, ticket);
+        while (segHint + 1 < bt.B && ticket >= pk[segHint + 1]) segHint++;     // a warp's tickets only grow
+        const int seg = segHint;
         const int n = st->np[seg][A.depth];
         const int iter = bt.iterBase + seg * bt.iterStride;
         const int numPackets = (n + 31) >> 5;
@@ -218,7 +234,14 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         PathRay r; r.o = mk(0, 0, 0); r.d = mk(0, 0, 0); r.inside = false; r.sdepth = 0.f;
         float tMin = FLT_MAX; int hitGeom = -1; V3 ipoint = mk(0, 0, 0), normal = mk(0, 0, 0);
         if (i < (unsigned)n) {
-            bm = P.bm[slot]; od = P.od[slot]; dr = P.dr[slot]; cp = P.cp[slot];     // four independent loads, one round trip
+            if (GEN) {          // first bounce: path i of an iteration is pixel i; nothing to read
+                V3 org, dir;
+                primaryRay(gen.cam, gen.ics.c[seg], (int)i, gen.focal, org, dir);
+                od = make_float4(org.x, org.y, org.z, 0.0f); dr = make_float4(dir.x, dir.y, dir.z, 0.0f);
+                cp = make_float4(1.0f, 1.0f, 1.0f, __int_as_float((int)i)); bm = make_int2(gen.traceDepth, 0);
+            } else {
+                bm = P.bm[slot]; od = P.od[slot]; dr = P.dr[slot]; cp = P.cp[slot];     // four independent loads, one round trip
+            }
             if (bm.x > 0) {
                 live = true;
                 r.o = mk(od.x, od.y, od.z); r.d = mk(dr.x, dr.y, dr.z); r.inside = dr.w != 0.0f; r.sdepth = od.w;
@@ -293,17 +316,29 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
                 float* px = accum + 3 * ((size_t)seg * bt.npix + pix);
                 px[0] = color.x; px[1] = color.y; px[2] = color.z;
             }
-            P.od[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.sdepth);
-            P.dr[slot] = make_float4(r.d.x, r.d.y, r.d.z, r.inside ? 1.0f : 0.0f);
-            P.cp[slot] = make_float4(color.x, color.y, color.z, cp.w);
-            bm.x = remaining;
-            P.bm[slot] = bm;
             alive = remaining > 0;
-        } else if (i < (unsigned)n) alive = bm.x > 0;
+            if ((A.stages & 8) && alive && accum) {     // last bounce of the loop: a path still alive is never gathered
+                float* px = accum + 3 * ((size_t)seg * bt.npix + __float_as_int(cp.w));
+                px[0] = 0.f; px[1] = 0.f; px[2] = 0.f;
+            }
+            // with compaction on, a finished path is never looked at again (its radiance went to accum above and the
+            // compaction reads the packet's alive mask, not the path): only survivors are written back
+            if (alive || !packetAlive) {
+                P.od[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.sdepth);
+                P.dr[slot] = make_float4(r.d.x, r.d.y, r.d.z, r.inside ? 1.0f : 0.0f);
+                P.cp[slot] = make_float4(color.x, color.y, color.z, cp.w);
+                bm.x = remaining;
+                P.bm[slot] = bm;
+            }
+        } else if (i < (unsigned)n) {
+            alive = bm.x > 0;
+            if (GEN) { P.od[slot] = od; P.dr[slot] = dr; P.cp[slot] = cp; P.bm[slot] = bm; }     // traceDepth <= 0
+        }
         unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
         unsigned liveMask = __ballot_sync(0xffffffffu, live);
         if (lane == 0) {
             if (packetCount) packetCount[seg * bt.capPackets + packet] = __popc(aliveMask);
+            if (packetAlive) packetAlive[seg * bt.capPackets + packet] = aliveMask;
             liveLocal += (unsigned)__popc(liveMask);
         }
       }
@@ -351,7 +386,8 @@ scanPacketsKernel(int* __restrict__ packetCountAll, LoopState* st, int depth, in
 }
 
 __global__ void __launch_bounds__(kThreads)
-compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset, LoopState* st, int depth, Batch bt)
+compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset, const unsigned* __restrict__ packetAlive,
+                     LoopState* st, int depth, Batch bt)
 {
     const unsigned lane = threadIdx.x & 31u;
     const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, numWarps = (gridDim.x * blockDim.x) >> 5;
@@ -361,13 +397,10 @@ compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset,
         for (int packet = warpId; packet < numPackets; packet += numWarps) {      // uniform work: static striding
             const unsigned i = (unsigned)packet * 32u + lane;
             const size_t slot = (size_t)seg * bt.cap + i;
-            int2 bm = make_int2(0, 0);
-            if (i < (unsigned)n) bm = P.bm[slot];
-            bool alive = i < (unsigned)n && bm.x != 0;          // is_zero_bounce, pathtrace.cu:103-110
-            unsigned mask = __ballot_sync(0xffffffffu, alive);
-            if (alive) {
+            const unsigned mask = packetAlive[seg * bt.capPackets + packet];   // remainingBounces != 0 (is_zero_bounce, pathtrace.cu:103-110)
+            if ((mask >> lane) & 1u) {
                 size_t dst = (size_t)seg * bt.cap + packetOffset[seg * bt.capPackets + packet] + __popc(mask & ((1u << lane) - 1u));
-                Q.od[dst] = P.od[slot]; Q.dr[dst] = P.dr[slot]; Q.cp[dst] = P.cp[slot]; Q.bm[dst] = bm;
+                Q.od[dst] = P.od[slot]; Q.dr[dst] = P.dr[slot]; Q.cp[dst] = P.cp[slot]; Q.bm[dst] = P.bm[slot];
             }
         }
     }
@@ -506,7 +539,7 @@ __global__ void unpackPathsKernel(PathSoA P, int n, kdpt_path_segment* __restric
 struct RenderBuffers {
     PathSoA A, B;
     LoopState* st;
-    int* packetCount;
+    int* packetCount; unsigned* packetAlive;
     unsigned* hist; int maxTiles;
     float* image;
     float* accum;
@@ -532,8 +565,9 @@ static int ensureRenderBuffers(kdpt_ctx* ctx, int n, int batch, RenderBuffers& r
     if (fresh) KDPT_CUDA(cudaMemsetAsync(ctx->scanTmp.p, 0, sizeof(LoopState), ctx->stream));
     rb.st = ctx->scanTmp.as<LoopState>();
     rb.cap = n; rb.capPackets = (n + 31) / 32 + 1;
-    if ((rc = ctx->keysTmp.ensure(sizeof(int) * (size_t)rb.capPackets * batch))) return rc;
+    if ((rc = ctx->keysTmp.ensure(2 * sizeof(int) * (size_t)rb.capPackets * batch))) return rc;
     rb.packetCount = ctx->keysTmp.as<int>();
+    rb.packetAlive = (unsigned*)(rb.packetCount + (size_t)rb.capPackets * batch);
     rb.maxTiles = (n + kSortTile - 1) / kSortTile + 1;
     if ((rc = ctx->hist.ensure(sizeof(unsigned) * 256 * (size_t)rb.maxTiles))) return rc;
     rb.hist = ctx->hist.as<unsigned>();
@@ -567,7 +601,7 @@ static int checkParams(const kdpt_params* p)
 }
 
 static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers& rb, PathSoA P, const Batch& bt, int depth,
-                        int stages, kdpt_intersection* dIsects, uint64_t& launches)
+                        int stages, kdpt_intersection* dIsects, uint64_t& launches, const GenArgs* gen)
 {
     SceneView S{ctx->scene.geoms.as<kdpt_geom>(), ctx->scene.numGeoms, ctx->scene.geomBounds.as<float4>(), ctx->scene.materials.as<kdpt_material>(), ctx->scene.numMaterials};
     BounceArgs A; A.iter = bt.iterBase; A.depth = depth; A.stages = stages; A.softness = p.softness; A.enableSss = p.enableSss;
@@ -575,12 +609,18 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
     int grid = ctx->numSMs * 8;
     cudaStream_t s = ctx->stream;
     int* pc = p.compaction ? rb.packetCount : nullptr;
+    unsigned* pa = p.compaction ? rb.packetAlive : nullptr;
+    static const GenArgs noGen{};
+#define KDPT_LAUNCH_BOUNCE(M)                                                                                                   \
+    if (gen) bounceKernel<M, true><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, *gen);   \
+    else bounceKernel<M, false><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, noGen)
     switch (p.mode) {
-    case KDPT_FULLSTACK: bounceKernel<KDPT_FULLSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
-    case KDPT_SHORTSTACK: bounceKernel<KDPT_SHORTSTACK><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
-    case KDPT_REF_T1: bounceKernel<KDPT_REF_T1><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
-    default: bounceKernel<KDPT_REF_T2><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, dIsects); break;
+    case KDPT_FULLSTACK: KDPT_LAUNCH_BOUNCE(KDPT_FULLSTACK); break;
+    case KDPT_SHORTSTACK: KDPT_LAUNCH_BOUNCE(KDPT_SHORTSTACK); break;
+    case KDPT_REF_T1: KDPT_LAUNCH_BOUNCE(KDPT_REF_T1); break;
+    default: KDPT_LAUNCH_BOUNCE(KDPT_REF_T2); break;
     }
+#undef KDPT_LAUNCH_BOUNCE
     launches++;
     KDPT_CUDA(cudaGetLastError());
     return KDPT_OK;
@@ -694,21 +734,27 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
         if (!sortThis) while (B < maxBatch && k + B < iter_count && !sorts(k + B)) B++;
         Batch bt; bt.B = B; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = iter_begin + k * iter_stride;
         bt.iterStride = iter_stride; bt.npix = n;
-        IterConsts ics;
-        for (int q = 0; q < B; q++) ics.c[q] = makeIterConst(bt.iterBase + q * iter_stride, p);
-        generateRaysKernel<<<(B * n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ics, bt, ctx->scene.traceDepth, p.focalLength, rb.A, rb.st, rb.accum);
+        GenArgs gen; memset(&gen, 0, sizeof gen);
+        gen.cam = ctx->scene.camera; gen.traceDepth = ctx->scene.traceDepth; gen.focal = p.focalLength;
+        for (int q = 0; q < B; q++) gen.ics.c[q] = makeIterConst(bt.iterBase + q * iter_stride, p);
+        if (maxBounces > 0) {
+            beginBatchKernel<<<1, 64, 0, s>>>(rb.st, B, n);     // the first bounce kernel generates the camera rays itself
+        } else {                                                // DEPTH <= 0: nothing is traced
+            generateRaysKernel<<<(B * n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, gen.ics, bt, ctx->scene.traceDepth, p.focalLength, rb.A, rb.st);
+            KDPT_CUDA(cudaMemsetAsync(rb.accum, 0, sizeof(float) * 3 * (size_t)n * B, s));
+        }
         launches++;
         PathSoA cur = rb.A, other = rb.B;
         for (int depth = 0; depth < maxBounces; depth++) {
-            int stages = KDPT_STAGE_INTERSECT | KDPT_STAGE_SHADE | (p.compaction ? 4 : 0);
+            int stages = KDPT_STAGE_INTERSECT | KDPT_STAGE_SHADE | (p.compaction ? 4 : 0) | ((p.compaction && depth == maxBounces - 1) ? 8 : 0);
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (timing) { if ((rc = nextEvent(t0)) || (rc = nextEvent(t1))) return rc; KDPT_CUDA(cudaEventRecord(t0, s)); }
-            if ((rc = launchBounce(ctx, p, rb, cur, bt, depth, stages, nullptr, launches))) return rc;
+            if ((rc = launchBounce(ctx, p, rb, cur, bt, depth, stages, nullptr, launches, depth == 0 ? &gen : nullptr))) return rc;
             if (timing) KDPT_CUDA(cudaEventRecord(t1, s));
             scanPacketsKernel<<<B, 1024, 0, s>>>(rb.packetCount, rb.st, depth, p.compaction, rb.capPackets);
             launches++;
             if (p.compaction) {
-                compactScatterKernel<<<grid, kThreads, 0, s>>>(cur, other, rb.packetCount, rb.st, depth, bt);
+                compactScatterKernel<<<grid, kThreads, 0, s>>>(cur, other, rb.packetCount, rb.packetAlive, rb.st, depth, bt);
                 launches++;
                 PathSoA t = cur; cur = other; other = t;
             }
@@ -765,7 +811,7 @@ int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_
     cudaStream_t s = ctx->stream;
     IterConsts ics; ics.c[0] = makeIterConst(iter, *params);
     Batch bt; bt.B = 1; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = iter; bt.iterStride = 1; bt.npix = n;
-    generateRaysKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ics, bt, ctx->scene.traceDepth, params->focalLength, rb.A, rb.st, nullptr);
+    generateRaysKernel<<<(n + 255) / 256, 256, 0, s>>>(ctx->scene.camera, ics, bt, ctx->scene.traceDepth, params->focalLength, rb.A, rb.st);
     unpackPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(rb.A, n, ctx->isects.as<kdpt_path_segment>());
     KDPT_CUDA(cudaGetLastError());
     KDPT_CUDA(cudaMemcpyAsync(out, ctx->isects.p, sizeof(kdpt_path_segment) * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -799,7 +845,7 @@ int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, k
     packPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(dPaths, n, rb.A, rb.st, depth);
     kdpt_params p = *params; p.compaction = 0;
     uint64_t launches = 0;
-    if ((rc = launchBounce(ctx, p, rb, rb.A, bt, depth, stages, dIs, launches))) return rc;
+    if ((rc = launchBounce(ctx, p, rb, rb.A, bt, depth, stages, dIs, launches, nullptr))) return rc;
     unpackPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(rb.A, n, dPaths);
     KDPT_CUDA(cudaGetLastError());
     KDPT_CUDA(cudaMemcpyAsync(paths, dPaths, pb, cudaMemcpyDeviceToHost, s));
