@@ -192,6 +192,9 @@ int kdpt_bind_image(kdpt_ctx* ctx, float* d_rgb);
 int kdpt_counters(kdpt_ctx* ctx, uint64_t* rayBounces, uint64_t* launches);
 /* accumulated radiance, W*H*3 floats (scene->state.image, pathtrace.cu:2631) */
 int kdpt_get_image(kdpt_ctx* ctx, float* rgb);
+/* restore an accumulation buffer saved with kdpt_get_image (checkpoint / resume of a long render: the reference has
+ * none — its buffer cannot be reloaded); continue with iter_begin = last rendered iteration + 1 */
+int kdpt_set_image(kdpt_ctx* ctx, const float* rgb);
 /* device pointer of that buffer (for an NCCL all-reduce issued by the caller) */
 int kdpt_image_device(kdpt_ctx* ctx, float** d_rgb, int* numFloats);
 

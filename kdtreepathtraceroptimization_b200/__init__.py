@@ -117,6 +117,7 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_bind_image.argtypes = [vp, vp]
     lib.kdpt_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     lib.kdpt_get_image.argtypes = [vp, vp]
+    lib.kdpt_set_image.argtypes = [vp, vp]
     lib.kdpt_image_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
     if lib.kdpt_abi_version() != 1:
         raise KdptError("libkdpt.so ABI version mismatch")
@@ -340,6 +341,14 @@ class Context:
         out = np.zeros((h, w, 3), np.float32)
         _check(self._lib.kdpt_get_image(self._h, _ptr(out)), "kdpt_get_image")
         return out
+
+    def set_image(self, rgb: np.ndarray):
+        """restore a saved accumulation buffer (checkpoint / resume)"""
+        a = np.ascontiguousarray(rgb, dtype=np.float32)
+        w, h = (int(x) for x in self.scene.camera['resolution'][0])
+        if a.size != w * h * 3:
+            raise KdptError("set_image: expected H x W x 3 floats")
+        _check(self._lib.kdpt_set_image(self._h, _ptr(a)), "kdpt_set_image")
 
     def image_device(self) -> tuple[int, int]:
         p = ctypes.c_void_p()

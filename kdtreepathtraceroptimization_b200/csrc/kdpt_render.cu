@@ -674,6 +674,17 @@ int kdpt_get_image(kdpt_ctx* ctx, float* rgb)
     return KDPT_OK;
 }
 
+int kdpt_set_image(kdpt_ctx* ctx, const float* rgb)
+{
+    if (!ctx || !rgb) { setError("kdpt_set_image: null argument"); return KDPT_ERR_ARG; }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensureImage(ctx);
+    if (rc) return rc;
+    KDPT_CUDA(cudaMemcpyAsync(ctx->boundImage ? (void*)ctx->boundImage : ctx->image.p, rgb, sizeof(float) * 3 * (size_t)ctx->pixelCount, cudaMemcpyHostToDevice, ctx->stream));
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KDPT_OK;
+}
+
 int kdpt_bind_image(kdpt_ctx* ctx, float* d_rgb)
 {
     if (!ctx) { setError("kdpt_bind_image: null context"); return KDPT_ERR_ARG; }

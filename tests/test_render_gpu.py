@@ -202,3 +202,17 @@ def test_headless_cli_matches_the_library(tmp_path):
     r = subprocess.run([exe, os.path.join(scenes, "cornell8.txt"), os.path.join(scenes, "stanford_bunny.obj"), "--spp", "1",
                         "--res", "32x32", "--out", str(png)], capture_output=True, text=True)
     assert r.returncode == 0 and png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
+
+
+def test_checkpoint_resume_is_bit_identical():
+    """render 1..4, save, restore into a fresh context, render 5..8 == render 1..8 in one go (kdpt_get_image /
+    kdpt_set_image; accumulation is iteration-ordered, so the result is bit-identical)"""
+    sc = _scene("cornell8_stanford_bunny.npz", 96, 96)
+    p = kdpt.default_params(mode=kdpt.FULLSTACK)
+    with kdpt.Context(sc) as a:
+        a.clear_image(); a.render(1, 8, 1, p); full = a.image()
+    with kdpt.Context(sc) as b:
+        b.clear_image(); b.render(1, 4, 1, p); ckpt = b.image()
+    with kdpt.Context(sc) as c:
+        c.set_image(ckpt); c.render(5, 4, 1, p); resumed = c.image()
+    assert full.tobytes() == resumed.tobytes()
