@@ -2,7 +2,9 @@
 #include "kdpt_flatten.h"
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <math.h>
+#include <thread>
 #include <unordered_map>
 
 namespace kdpt {
@@ -98,13 +100,33 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
 
     // canonical index = first TriBare entry holding identical 76 bytes (what kdpt_hit.tri reports)
     std::vector<int> canon((size_t)numTris);
+    unsigned hwc = std::thread::hardware_concurrency();
+    const int nthreads = numTris < (1 << 16) ? 1 : (int)(hwc == 0 ? 4 : (hwc > 32 ? 32 : hwc));
     {
-        std::unordered_map<TriKey, int, TriKeyHash> first;
-        first.reserve((size_t)numTris);
-        for (int i = 0; i < numTris; i++) {
-            TriKey k; memcpy(k.w, &tris[i], sizeof k.w);
-            auto it = first.find(k);
-            if (it == first.end()) { first.emplace(k, i); canon[i] = i; } else canon[i] = it->second;
+        // sharded by hash so that every shard is built by one thread scanning in index order (first occurrence wins)
+        std::vector<uint64_t> hashes((size_t)numTris);
+        auto hashRange = [&](int lo, int hi) {
+            TriKeyHash H;
+            for (int i = lo; i < hi; i++) { TriKey k; memcpy(k.w, &tris[i], sizeof k.w); hashes[i] = (uint64_t)H(k); }
+        };
+        auto shard = [&](int t) {
+            std::unordered_map<TriKey, int, TriKeyHash> first;
+            first.reserve((size_t)numTris / nthreads + 16);
+            for (int i = 0; i < numTris; i++) {
+                if ((int)((hashes[i] >> 20) % (uint64_t)nthreads) != t) continue;
+                TriKey k; memcpy(k.w, &tris[i], sizeof k.w);
+                auto it = first.find(k);
+                if (it == first.end()) { first.emplace(k, i); canon[i] = i; } else canon[i] = it->second;
+            }
+        };
+        if (nthreads == 1) { hashRange(0, numTris); shard(0); }
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthreads; t++) th.emplace_back(hashRange, (int)((long long)numTris * t / nthreads), (int)((long long)numTris * (t + 1) / nthreads));
+            for (auto& t : th) t.join();
+            th.clear();
+            for (int t = 0; t < nthreads; t++) th.emplace_back(shard, t);
+            for (auto& t : th) t.join();
         }
     }
     // Leaf-local culling structure. The reference builder stops at depth 14 or as soon as a split keeps every
@@ -125,12 +147,39 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
         const float* x = &t.x1;          // x1 x2 x3 y1 y2 y3 z1 z2 z3
         return x[3 * a + k];
     };
-    for (int nId = 0; nId < numNodes; nId++) {
-        HostNode& h = out.nodes[nId];
-        if ((h.w & 3u) != 3u) continue;
-        h.z = 0xffffffffu;
+    // pass 1: which leaves are chunked and where their chunks / groups go
+    std::vector<int> chunkedLeaves;
+    {
+        size_t nChunks = 0, nSupers = 0;
+        for (int nId = 0; nId < numNodes; nId++) {
+            HostNode& h = out.nodes[nId];
+            if ((h.w & 3u) != 3u) continue;
+            h.z = 0xffffffffu;
+            const int count = (int)h.y;
+            if (count < kChunkMinLeaf) continue;
+            h.z = (uint32_t)nChunks;
+            chunkedLeaves.push_back(nId);
+            const size_t nch = ((size_t)count + 31) / 32;
+            nChunks += nch;
+            if ((int)nch >= kSuperMinChunks) nSupers += (nch + 31) / 32;
+        }
+        out.chunkLo.resize(nChunks); out.chunkHi.resize(nChunks);
+        out.superLo.resize(nSupers); out.superHi.resize(nSupers);
+    }
+    std::vector<size_t> superOfLeaf(chunkedLeaves.size());
+    {
+        size_t acc = 0;
+        for (size_t q = 0; q < chunkedLeaves.size(); q++) {
+            const size_t nch = ((size_t)out.nodes[chunkedLeaves[q]].y + 31) / 32;
+            superOfLeaf[q] = acc;
+            if ((int)nch >= kSuperMinChunks) acc += (nch + 31) / 32;
+        }
+    }
+    // pass 2: leaves are independent -> spread over the host cores
+    auto doLeaf = [&](size_t q) {
+        const HostNode& h = out.nodes[chunkedLeaves[q]];
         const int start = (int)h.x, count = (int)h.y;
-        if (count < kChunkMinLeaf) continue;
+        const size_t firstChunk = h.z;
         // Morton order of centroids inside the leaf's own centroid bounds
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         std::vector<float> cen(3 * (size_t)count);
@@ -143,62 +192,77 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
         std::vector<std::pair<uint32_t, int>> keys((size_t)count);
         for (int j = 0; j < count; j++) {
             uint32_t code = 0;
-            uint32_t q[3];
+            uint32_t qv[3];
             for (int a = 0; a < 3; a++) {
                 float ext = hi[a] - lo[a];
                 float f = ext > 0 ? (cen[3 * (size_t)j + a] - lo[a]) / ext : 0.f;
-                int v = (int)(f * 1023.0f); q[a] = (uint32_t)(v < 0 ? 0 : (v > 1023 ? 1023 : v));
+                int v = (int)(f * 1023.0f); qv[a] = (uint32_t)(v < 0 ? 0 : (v > 1023 ? 1023 : v));
             }
-            for (int b = 9; b >= 0; b--) for (int a = 0; a < 3; a++) code = (code << 1) | ((q[a] >> b) & 1u);
+            for (int b = 9; b >= 0; b--) for (int a = 0; a < 3; a++) code = (code << 1) | ((qv[a] >> b) & 1u);
             keys[j] = std::make_pair(code, start + j);
         }
         std::sort(keys.begin(), keys.end());
         for (int j = 0; j < count; j++) order[start + j] = keys[j].second;
-        h.z = (uint32_t)out.chunkLo.size();
-        const size_t firstChunk = out.chunkLo.size();
-        for (int c0 = 0; c0 < count; c0 += 32) {
+        size_t nch = 0;
+        for (int c0 = 0; c0 < count; c0 += 32, nch++) {
             float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
             for (int j = c0; j < count && j < c0 + 32; j++)
                 for (int k = 0; k < 3; k++)
                     for (int a = 0; a < 3; a++) { float x = vert(order[start + j], k, a); blo[a] = fminf(blo[a], x); bhi[a] = fmaxf(bhi[a], x); }
-            out.chunkLo.push_back(HostF4{blo[0] - pad, blo[1] - pad, blo[2] - pad, asFloat(-1)});
-            out.chunkHi.push_back(HostF4{bhi[0] + pad, bhi[1] + pad, bhi[2] + pad, 0.f});
+            out.chunkLo[firstChunk + nch] = HostF4{blo[0] - pad, blo[1] - pad, blo[2] - pad, asFloat(-1)};
+            out.chunkHi[firstChunk + nch] = HostF4{bhi[0] + pad, bhi[1] + pad, bhi[2] + pad, 0.f};
         }
         // second level for very fat leaves: one box per 32 consecutive chunks (1024 triangles); the first chunk's
-        // lo.w carries the index of the leaf's first super box (-1: none)
-        const size_t nch = out.chunkLo.size() - firstChunk;
+        // lo.w carries the index of the leaf's first group box (-1: none)
         if ((int)nch >= kSuperMinChunks) {
-            out.chunkLo[firstChunk].w = asFloat((int)out.superLo.size());
-            for (size_t g = 0; g < nch; g += 32) {
+            size_t sp = superOfLeaf[q];
+            out.chunkLo[firstChunk].w = asFloat((int)sp);
+            for (size_t g = 0; g < nch; g += 32, sp++) {
                 float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
                 for (size_t c = g; c < nch && c < g + 32; c++) {
                     const HostF4& l = out.chunkLo[firstChunk + c]; const HostF4& u = out.chunkHi[firstChunk + c];
                     blo[0] = fminf(blo[0], l.x); blo[1] = fminf(blo[1], l.y); blo[2] = fminf(blo[2], l.z);
                     bhi[0] = fmaxf(bhi[0], u.x); bhi[1] = fmaxf(bhi[1], u.y); bhi[2] = fmaxf(bhi[2], u.z);
                 }
-                out.superLo.push_back(HostF4{blo[0], blo[1], blo[2], 0.f});
-                out.superHi.push_back(HostF4{bhi[0], bhi[1], bhi[2], 0.f});
+                out.superLo[sp] = HostF4{blo[0], blo[1], blo[2], 0.f};
+                out.superHi[sp] = HostF4{bhi[0], bhi[1], bhi[2], 0.f};
             }
         }
+    };
+    if (nthreads == 1 || chunkedLeaves.size() < 2) { for (size_t q = 0; q < chunkedLeaves.size(); q++) doLeaf(q); }
+    else {
+        std::atomic<size_t> nextLeaf(0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++)
+            th.emplace_back([&]() { for (size_t q = nextLeaf.fetch_add(1); q < chunkedLeaves.size(); q = nextLeaf.fetch_add(1)) doLeaf(q); });
+        for (auto& t : th) t.join();
     }
     out.numChunks = (int)out.chunkLo.size();
 
     out.triA.resize(numTris); out.triB.resize(numTris); out.triC.resize(numTris);
     out.nrmA.resize(numTris); out.nrmB.resize(numTris); out.nrmC.resize(numTris);
     out.triOrig.resize(numTris);
-    for (int i = 0; i < numTris; i++) {
-        const int src = order[i];
-        const kdpt_tri_bare& t = tris[src];
-        // e1 = v1 - v0, e2 = v2 - v0: binary32 subtractions, the same the reference performs per test
-        float e1x = t.x2 - t.x1, e1y = t.y2 - t.y1, e1z = t.z2 - t.z1;
-        float e2x = t.x3 - t.x1, e2y = t.y3 - t.y1, e2z = t.z3 - t.z1;
-        out.triA[i] = HostF4{t.x1, t.y1, t.z1, e1x};
-        out.triB[i] = HostF4{e1y, e1z, e2x, e2y};
-        out.triC[i] = HostF2{e2z, asFloat(canon[src])};
-        out.nrmA[i] = HostF4{t.nx1, t.ny1, t.nz1, t.nx2};
-        out.nrmB[i] = HostF4{t.ny2, t.nz2, t.nx3, t.ny3};
-        out.nrmC[i] = HostF2{t.nz3, asFloat(t.mtlIdx)};
-        out.triOrig[i] = src;
+    auto fill = [&](int lo, int hi) {
+        for (int i = lo; i < hi; i++) {
+            const int src = order[i];
+            const kdpt_tri_bare& t = tris[src];
+            // e1 = v1 - v0, e2 = v2 - v0: binary32 subtractions, the same the reference performs per test
+            float e1x = t.x2 - t.x1, e1y = t.y2 - t.y1, e1z = t.z2 - t.z1;
+            float e2x = t.x3 - t.x1, e2y = t.y3 - t.y1, e2z = t.z3 - t.z1;
+            out.triA[i] = HostF4{t.x1, t.y1, t.z1, e1x};
+            out.triB[i] = HostF4{e1y, e1z, e2x, e2y};
+            out.triC[i] = HostF2{e2z, asFloat(canon[src])};
+            out.nrmA[i] = HostF4{t.nx1, t.ny1, t.nz1, t.nx2};
+            out.nrmB[i] = HostF4{t.ny2, t.nz2, t.nx3, t.ny3};
+            out.nrmC[i] = HostF2{t.nz3, asFloat(t.mtlIdx)};
+            out.triOrig[i] = src;
+        }
+    };
+    if (nthreads == 1) fill(0, numTris);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(fill, (int)((long long)numTris * t / nthreads), (int)((long long)numTris * (t + 1) / nthreads));
+        for (auto& t : th) t.join();
     }
     return true;
 }

@@ -19,6 +19,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace kdpt {
@@ -383,11 +384,36 @@ struct Builder {
         const int level = depth % 3;
         const double c = (double)center[level];
         std::vector<int> L, R;
-        L.reserve(num / 2 + 16); R.reserve(num / 2 + 16);
-        for (int i = 0; i < num; i++) {
-            int t = tris[i];
-            if ((double)tmin[3 * (size_t)t + level] < c + 0.0001) L.push_back(t);
-            if ((double)tmax[3 * (size_t)t + level] >= c - 0.0001) R.push_back(t);
+        if (num < (1 << 17)) {
+            L.reserve(num / 2 + 16); R.reserve(num / 2 + 16);
+            for (int i = 0; i < num; i++) {
+                int t = tris[i];
+                if ((double)tmin[3 * (size_t)t + level] < c + 0.0001) L.push_back(t);
+                if ((double)tmax[3 * (size_t)t + level] >= c - 0.0001) R.push_back(t);
+            }
+        } else {
+            // big nodes (the top of a multi-million-triangle tree): the classification is a per-triangle predicate, so
+            // it is split over the host cores; pieces are concatenated in order, which keeps the lists (and therefore
+            // every leaf's triangle order and every node ID) identical to the sequential build
+            unsigned hw = std::thread::hardware_concurrency();
+            const int nt = (int)(hw == 0 ? 4 : (hw > 32 ? 32 : hw));
+            std::vector<std::vector<int>> Ls(nt), Rs(nt);
+            std::vector<std::thread> th;
+            for (int k = 0; k < nt; k++)
+                th.emplace_back([&, k]() {
+                    const int lo = (int)((long long)num * k / nt), hi = (int)((long long)num * (k + 1) / nt);
+                    Ls[k].reserve((hi - lo) / 2 + 16); Rs[k].reserve((hi - lo) / 2 + 16);
+                    for (int i = lo; i < hi; i++) {
+                        int t = tris[i];
+                        if ((double)tmin[3 * (size_t)t + level] < c + 0.0001) Ls[k].push_back(t);
+                        if ((double)tmax[3 * (size_t)t + level] >= c - 0.0001) Rs[k].push_back(t);
+                    }
+                });
+            for (auto& t : th) t.join();
+            size_t nl = 0, nr = 0;
+            for (int k = 0; k < nt; k++) { nl += Ls[k].size(); nr += Rs[k].size(); }
+            L.reserve(nl); R.reserve(nr);
+            for (int k = 0; k < nt; k++) { L.insert(L.end(), Ls[k].begin(), Ls[k].end()); R.insert(R.end(), Rs[k].begin(), Rs[k].end()); }
         }
         if ((int)L.size() == num || (int)R.size() == num) { leaf(id, tris.data(), num); return; }
         std::vector<int>().swap(tris);              // interior nodes drop their list (KDnode.cpp:246-247)
