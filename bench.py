@@ -53,6 +53,15 @@ TRACE_WORKLOADS = {
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[workload]
+        return t["dram_bytes_per_launch"], t["kernel"]
+    except Exception:
+        return None, None
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -73,7 +82,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -278,7 +287,8 @@ def run_trace_workload(args):
                                                           "l2": "working set (tree 0.9 GB + rays/hits 0.9 GB) exceeds L2; no flush"},
                           "clocks": clk, "gpu_launches": K,
                           "e2e": {"value": world * nrays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": nrays * 24, "d2h_bytes_per_step": nrays * 32},
-                          "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                          "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                       "traffic": measured_traffic(args.workload)[0],
                                        "kernel": "traceKernel<fullstack>", "avg_launch_ms": ms / K, "algorithmic_bytes_per_ray": bpr,
                                        "V_nodes_per_ray": V, "T_tris_per_ray": T, "peak_source": peak_src},
                           "cpu_baseline": {"value": 20000 / dt1 / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
@@ -452,7 +462,9 @@ def main():
             launch_ms = st["intersect_ms"] / nb
             bytes_per_launch = ab["bytes_per_ray_bounce"] * st["ray_bounces"] / nb
             achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            traffic, traffic_kernel = measured_traffic(args.workload)
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_of": traffic_kernel,
                     "kernel": "bounceKernel<%s>" % WORKLOADS[args.workload][3], "avg_launch_ms": launch_ms,
                     "kernel_share_of_step": st["intersect_ms"] / st["total_ms"],
                     "algorithmic_bytes_per_ray_bounce": ab["bytes_per_ray_bounce"], "V_nodes_per_ray": ab["V"], "T_tris_per_ray": ab["T"],
