@@ -15,8 +15,11 @@ constexpr int kCoopMin = KDPT_COOP_MIN;   // leaves with at least this many tria
 // Persistent threads: a fixed grid (a multiple of the SM count) whose warps pull 32-ray packets from a global
 // counter until the batch is drained, so a warp stuck in a fat leaf does not hold back the rest of its block's
 // share of the batch.
+#ifndef KDPT_TRACE_MIN_BLOCKS
+#define KDPT_TRACE_MIN_BLOCKS 7    // <= 72 registers: 28 warps per SM (measured best of 4..8 on dragon_5 and the 1 M / 10 M soups)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, KDPT_TRACE_MIN_BLOCKS)
 traceKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__ tMinIn, int n,
             kdpt_hit* __restrict__ hits, unsigned* __restrict__ counter)
 {
