@@ -430,36 +430,43 @@ compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset,
 // ---- stable LSD radix sort by materialIdHit (replaces thrust::sort, pathtrace.cu:2600-2606) -----------------------
 __device__ __forceinline__ unsigned sortDigit(int materialIdHit, int shift) { return ((unsigned)(materialIdHit + 1) >> shift) & 255u; }
 
+// All three kernels work per batched iteration (segment `seg` of the path arrays, its own histogram block of
+// 256 x maxTiles counters): paths are only ever reordered inside their own iteration.
 __global__ void __launch_bounds__(kSortTile)
-sortHistKernel(PathSoA P, LoopState* st, int depth, int shift, unsigned* __restrict__ hist, int maxTiles)
+sortHistKernel(PathSoA P, LoopState* st, int depth, int shift, unsigned* __restrict__ histAll, int maxTiles, Batch bt)
 {
     __shared__ unsigned h[256];
-    const int n = st->np[0][depth];                // the sort runs on single-iteration batches only
-    const int numTiles = (n + kSortTile - 1) / kSortTile;
-    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        if (threadIdx.x < 256) h[threadIdx.x] = 0;
-        __syncthreads();
-        int i = tile * kSortTile + threadIdx.x;
-        if (i < n) atomicAdd(&h[sortDigit(P.bm[i].y, shift)], 1u);
-        __syncthreads();
-        if (threadIdx.x < 256) hist[threadIdx.x * maxTiles + tile] = h[threadIdx.x];
-        __syncthreads();
+    for (int seg = 0; seg < bt.B; seg++) {
+        const int n = st->np[seg][depth];
+        const int numTiles = (n + kSortTile - 1) / kSortTile;
+        unsigned* hist = histAll + (size_t)seg * 256 * maxTiles;
+        for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+            if (threadIdx.x < 256) h[threadIdx.x] = 0;
+            __syncthreads();
+            int i = tile * kSortTile + threadIdx.x;
+            if (i < n) atomicAdd(&h[sortDigit(P.bm[(size_t)seg * bt.cap + i].y, shift)], 1u);
+            __syncthreads();
+            if (threadIdx.x < 256) hist[threadIdx.x * maxTiles + tile] = h[threadIdx.x];
+            __syncthreads();
+        }
     }
 }
-// exclusive scan over (digit-major, tile-minor) counts; one block
+// exclusive scan over (digit-major, tile-minor) counts; one block per batched iteration
 __global__ void __launch_bounds__(1024)
-sortScanKernel(LoopState* st, int depth, unsigned* __restrict__ hist, int maxTiles)
+sortScanKernel(LoopState* st, int depth, unsigned* __restrict__ histAll, int maxTiles)
 {
     __shared__ unsigned warpSums[32];
     __shared__ unsigned carry;
-    const int n = st->np[0][depth];                // the sort runs on single-iteration batches only
+    const int seg = blockIdx.x;
+    unsigned* hist = histAll + (size_t)seg * 256 * maxTiles;
+    const int n = st->np[seg][depth];
     const int numTiles = (n + kSortTile - 1) / kSortTile;
     const int total = 256 * numTiles;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < total; base += 1024) {
         int k = base + threadIdx.x;
-        int digit = k / numTiles, tile = k - digit * numTiles;
+        int digit = k / (numTiles > 0 ? numTiles : 1), tile = k - digit * numTiles;
         unsigned v = k < total ? hist[digit * maxTiles + tile] : 0u;
         unsigned incl = v;
 #pragma unroll
@@ -481,29 +488,33 @@ sortScanKernel(LoopState* st, int depth, unsigned* __restrict__ hist, int maxTil
     }
 }
 __global__ void __launch_bounds__(kSortTile)
-sortScatterKernel(PathSoA P, PathSoA Q, LoopState* st, int depth, int shift, const unsigned* __restrict__ hist, int maxTiles)
+sortScatterKernel(PathSoA P, PathSoA Q, LoopState* st, int depth, int shift, const unsigned* __restrict__ histAll, int maxTiles, Batch bt)
 {
     __shared__ unsigned short warpDigitCount[kSortTile / 32][256];
-    const int n = st->np[0][depth];                // the sort runs on single-iteration batches only
-    const int numTiles = (n + kSortTile - 1) / kSortTile;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        for (int k = threadIdx.x; k < (kSortTile / 32) * 256; k += blockDim.x) (&warpDigitCount[0][0])[k] = 0;
-        __syncthreads();
-        int i = tile * kSortTile + threadIdx.x;
-        bool valid = i < n;
-        int2 bm = valid ? P.bm[i] : make_int2(0, 0);
-        unsigned digit = valid ? sortDigit(bm.y, shift) : 0xffffffffu;
-        unsigned peers = __match_any_sync(0xffffffffu, digit);
-        unsigned rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) warpDigitCount[warp][digit] = (unsigned short)__popc(peers);
-        __syncthreads();
-        if (valid) {
-            unsigned dst = hist[digit * maxTiles + tile] + rank;
-            for (unsigned w = 0; w < warp; w++) dst += warpDigitCount[w][digit];
-            Q.od[dst] = P.od[i]; Q.dr[dst] = P.dr[i]; Q.cp[dst] = P.cp[i]; Q.bm[dst] = bm;
+    for (int seg = 0; seg < bt.B; seg++) {
+        const int n = st->np[seg][depth];
+        const int numTiles = (n + kSortTile - 1) / kSortTile;
+        const unsigned* hist = histAll + (size_t)seg * 256 * maxTiles;
+        const size_t base = (size_t)seg * bt.cap;
+        for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+            for (int k = threadIdx.x; k < (kSortTile / 32) * 256; k += blockDim.x) (&warpDigitCount[0][0])[k] = 0;
+            __syncthreads();
+            int i = tile * kSortTile + threadIdx.x;
+            bool valid = i < n;
+            int2 bm = valid ? P.bm[base + i] : make_int2(0, 0);
+            unsigned digit = valid ? sortDigit(bm.y, shift) : 0xffffffffu;
+            unsigned peers = __match_any_sync(0xffffffffu, digit);
+            unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank == 0) warpDigitCount[warp][digit] = (unsigned short)__popc(peers);
+            __syncthreads();
+            if (valid) {
+                unsigned dst = hist[digit * maxTiles + tile] + rank;
+                for (unsigned w = 0; w < warp; w++) dst += warpDigitCount[w][digit];
+                Q.od[base + dst] = P.od[base + i]; Q.dr[base + dst] = P.dr[base + i]; Q.cp[base + dst] = P.cp[base + i]; Q.bm[base + dst] = bm;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -590,7 +601,7 @@ static int ensureRenderBuffers(kdpt_ctx* ctx, int n, int batch, RenderBuffers& r
     rb.packetCount = ctx->keysTmp.as<int>();
     rb.packetAlive = (unsigned*)(rb.packetCount + (size_t)rb.capPackets * batch);
     rb.maxTiles = (n + kSortTile - 1) / kSortTile + 1;
-    if ((rc = ctx->hist.ensure(sizeof(unsigned) * 256 * (size_t)rb.maxTiles))) return rc;
+    if ((rc = ctx->hist.ensure(sizeof(unsigned) * 256 * (size_t)rb.maxTiles * batch))) return rc;
     rb.hist = ctx->hist.as<unsigned>();
     rb.image = ctx->boundImage ? ctx->boundImage : ctx->image.as<float>();
     rb.accum = nullptr;
@@ -734,10 +745,9 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     if ((rc = ensureImage(ctx))) return rc;
     const kdpt_params& p = *params;
     const int n = ctx->pixelCount;
-    // iterations per launch: bounded by kMaxBatch and by ~1.5 GB of path state; the material sort is per iteration
+    // iterations per launch: bounded by kMaxBatch and by ~1.5 GB of path state
     int maxBatch = kMaxBatch;
     while (maxBatch > 1 && (size_t)maxBatch * n * 128 > ((size_t)3 << 29)) maxBatch >>= 1;
-    if (p.sortByMaterial == 2) maxBatch = 1;
     if (iter_count < maxBatch) maxBatch = iter_count > 0 ? iter_count : 1;
     RenderBuffers rb;
     if ((rc = ensureRenderBuffers(ctx, n, maxBatch, rb, true))) return rc;
@@ -759,11 +769,12 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     // remainingBounces starts at traceDepth and drops every bounce, so nothing survives min(8, traceDepth) bounces
     const int maxBounces = ctx->scene.traceDepth < kMaxBounces ? (ctx->scene.traceDepth < 0 ? 0 : ctx->scene.traceDepth) : kMaxBounces;
     for (int k = 0; k < iter_count;) {
-        // the reference sorts only in iteration 2 (pathtrace.cu:2600): that iteration gets a batch of its own
+        // a batch is sorted as a whole or not at all: the reference sorts only in iteration 2 (pathtrace.cu:2600), so
+        // with sortByMaterial == 1 that iteration gets a batch of its own
         auto sorts = [&](int kk) { int it = iter_begin + kk * iter_stride; return p.sortByMaterial == 2 || (p.sortByMaterial == 1 && it == 2); };
         int B = 1;
         const bool sortThis = sorts(k);
-        if (!sortThis) while (B < maxBatch && k + B < iter_count && !sorts(k + B)) B++;
+        while (B < maxBatch && k + B < iter_count && sorts(k + B) == sortThis && (p.sortByMaterial != 1 || !sortThis)) B++;
         Batch bt; bt.B = B; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = iter_begin + k * iter_stride;
         bt.iterStride = iter_stride; bt.npix = n;
         GenArgs gen; memset(&gen, 0, sizeof gen);
@@ -792,9 +803,9 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
             }
             if (sortThis) {
                 for (int pass = 0; pass < sortPasses; pass++) {
-                    sortHistKernel<<<grid, kSortTile, 0, s>>>(cur, rb.st, depth + 1, 8 * pass, rb.hist, rb.maxTiles);
-                    sortScanKernel<<<1, 1024, 0, s>>>(rb.st, depth + 1, rb.hist, rb.maxTiles);
-                    sortScatterKernel<<<grid, kSortTile, 0, s>>>(cur, other, rb.st, depth + 1, 8 * pass, rb.hist, rb.maxTiles);
+                    sortHistKernel<<<grid, kSortTile, 0, s>>>(cur, rb.st, depth + 1, 8 * pass, rb.hist, rb.maxTiles, bt);
+                    sortScanKernel<<<B, 1024, 0, s>>>(rb.st, depth + 1, rb.hist, rb.maxTiles);
+                    sortScatterKernel<<<grid, kSortTile, 0, s>>>(cur, other, rb.st, depth + 1, 8 * pass, rb.hist, rb.maxTiles, bt);
                     launches += 3;
                     PathSoA t = cur; cur = other; other = t;
                 }
