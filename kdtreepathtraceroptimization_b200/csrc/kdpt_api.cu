@@ -66,16 +66,6 @@ static int upload(DeviceBuffer& buf, const std::vector<T>& v, const T** devPtr, 
     return KDPT_OK;
 }
 
-static int ensurePinned(void** p, size_t* have, size_t need)
-{
-    if (*p && *have >= need) return KDPT_OK;
-    if (*p) cudaFreeHost(*p);
-    *p = nullptr; *have = 0;
-    KDPT_CUDA(cudaMallocHost(p, need + need / 4));
-    *have = need + need / 4;
-    return KDPT_OK;
-}
-
 } // namespace kdpt
 
 using namespace kdpt;
@@ -124,8 +114,6 @@ int kdpt_destroy(kdpt_ctx* ctx)
                             &ctx->hits, &ctx->counter, &ctx->image, &ctx->pathsA, &ctx->pathsB, &ctx->isects,
                             &ctx->scanTmp, &ctx->keysTmp, &ctx->hist, &ctx->accum};
     for (auto* b : bufs) b->release();
-    if (ctx->pinnedIn) cudaFreeHost(ctx->pinnedIn);
-    if (ctx->pinnedOut) cudaFreeHost(ctx->pinnedOut);
     cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev2, ctx->ev3};
     for (auto e : evs) if (e) cudaEventDestroy(e);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);

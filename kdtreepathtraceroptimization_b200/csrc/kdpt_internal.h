@@ -49,8 +49,6 @@ struct kdpt_ctx {
     kdpt::SceneDev scene;
     // traversal scratch
     kdpt::DeviceBuffer rays, tmin, hits, counter;
-    void* pinnedIn = nullptr; size_t pinnedInBytes = 0;
-    void* pinnedOut = nullptr; size_t pinnedOutBytes = 0;
     // render loop state
     kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist, accum;
     int pixelCount = 0;

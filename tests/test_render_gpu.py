@@ -216,3 +216,33 @@ def test_checkpoint_resume_is_bit_identical():
     with kdpt.Context(sc) as c:
         c.set_image(ckpt); c.render(5, 4, 1, p); resumed = c.image()
     assert full.tobytes() == resumed.tobytes()
+
+
+@pytest.mark.parametrize("variant", ["no_mesh", "no_geoms", "depth1", "depth10", "odd_res", "no_compaction_depth10"])
+def test_render_edge_cases_match_oracle(oracle, variant):
+    """scene without a mesh, mesh without analytic geoms, DEPTH 1 and DEPTH 10 (beyond the reference's 8-bounce cap:
+    survivors are dropped with compaction on, added by finalGather with it off), resolution not a multiple of 32"""
+    sc = _scene("cornell_sphere_low_1.npz", 96, 64)
+    kw = dict(mode=kdpt.FULLSTACK, sortByMaterial=0)
+    if variant == "no_mesh":
+        sc.nodes = np.zeros(0, kdpt.NODE); sc.tris = np.zeros(0, kdpt.TRI)
+    elif variant == "no_geoms":
+        sc.geoms = np.zeros(0, kdpt.GEOM)
+    elif variant == "depth1":
+        sc.trace_depth = 1
+    elif variant == "depth10":
+        sc.trace_depth = 10
+    elif variant == "odd_res":
+        sc = _scene("cornell_sphere_low_1.npz", 77, 53)
+    elif variant == "no_compaction_depth10":
+        sc.trace_depth = 10; kw["compaction"] = 0
+    p = kdpt.default_params(**kw)
+    with kdpt.Context(sc) as ctx:
+        ctx.clear_image()
+        st = ctx.render(1, 3, 1, p)
+        g = ctx.image()
+    o, total = _oracle_render(oracle, sc, p, [1, 2, 3])
+    assert abs(int(st['ray_bounces']) - int(total)) <= max(2, int(2e-3 * total)), (st['ray_bounces'], total)
+    assert (np.abs(g - o).max(2) < 1e-3).mean() > 0.99
+    if variant != "no_geoms":
+        assert o.sum() > 0
