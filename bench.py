@@ -176,7 +176,7 @@ def cpu_iteration_runner(sc, params):
     return "port", run, cores
 
 
-def algorithmic_bytes_per_ray(sc, params):
+def algorithmic_bytes_from_oracle(sc, params):
     """bytes(ray) = 32 (ray in) + 16 (hit out) + 16 V + 4 L + 48 T, plus per path-bounce 2x56 B path
     state and 24 B of accumulation; V/L/T from the instrumented CPU traversal over the rays of iteration 1."""
     from conftest import KO_CTR, P, ko_params, ko_scene
@@ -195,6 +195,11 @@ def algorithmic_bytes_per_ray(sc, params):
     traversal = 32 + 16 + 16 * V + 4 * T + 48 * T
     return dict(V=V, T=T, traversal_bytes=traversal, path_bytes=2 * 56 + 24, bytes_per_ray_bounce=traversal + 2 * 56 + 24,
                 ray_bounces_iter1=int(tot))
+
+
+def algorithmic_bytes_per_ray(workload):
+    """the committed per-ray figures (profiles/algorithmic_bytes.json, regenerated by tools/algorithmic_bytes.py)"""
+    return json.load(open(os.path.join(ROOT, "profiles", "algorithmic_bytes.json")))[workload]
 
 
 def run_trace_workload(args):
@@ -275,9 +280,8 @@ def run_trace_workload(args):
     ms, e2e_s = float(t[0]), float(t[1])
     if rank == 0:
         value = world * nrays * K / (ms * 1e-3) / 1e6
-        dt, ctr = cpu_run(KO_STACK_T1, 20000)
-        V = float(ctr['nodes']) / 20000; T = float(ctr['tris']) / 20000
-        bpr = 48 + 16 * V + 52 * T
+        ab = algorithmic_bytes_per_ray(args.workload)
+        V, T, bpr = ab["V"], ab["T"], ab["bytes_per_ray_bounce"]
         peak, peak_src = peak_hbm()
         achieved = bpr * nrays / (ms / K * 1e-3) / 1e9
         dt1, _ = cpu_run(KO_T1, 20000)
@@ -453,8 +457,7 @@ def main():
         peak, peak_src = peak_hbm()
         roof = None; cpu = None
         try:
-            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
-            ab = algorithmic_bytes_per_ray(sc, params)
+            ab = algorithmic_bytes_per_ray(args.workload)
             pt = kdpt.default_params(); ctypes.memmove(ctypes.byref(pt), ctypes.byref(params), ctypes.sizeof(pt)); pt.testingmode = 1
             ctx.render(1, S, 1, pt)
             st = ctx.render(1 + S, S, 1, pt)
@@ -471,7 +474,7 @@ def main():
                     "peak_source": peak_src,
                     "note": "tree + triangles of this workload are %d KB, i.e. L1/L2-resident: the HBM figure is the "
                             "contract's denominator, not the physical bound (see DESIGN.md)" % (ctx.tree_info()["device_bytes"] // 1024)}
-        except Exception as e:      # the roofline needs the oracle's counters; never let it kill the bench line
+        except Exception as e:      # never let the roofline bookkeeping kill the bench line
             roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
