@@ -333,7 +333,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kdpt", choices=["kdpt", "reference"])
     ap.add_argument("--workload", default="bunny", choices=sorted(WORKLOADS) + sorted(TRACE_WORKLOADS))
@@ -403,7 +403,6 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clk = clocks.stop()
     rb1, l1 = ctx.counters()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms, float(rb1 - rb0)], dtype=torch.float64, device="cuda")
@@ -444,6 +443,7 @@ def main():
         c2.close()
         if k > 0:
             e2e_s += dt; e2e_rays += st["ray_bounces"]
+    clk = clocks.stop()         # sampled over the device-timed steps and the end-to-end steps
     et = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device="cuda")
     if world > 1:
         emax = et.clone(); dist.all_reduce(emax, op=dist.ReduceOp.MAX)
