@@ -339,6 +339,8 @@ def main():
     ap.add_argument("--workload", default="bunny", choices=sorted(WORKLOADS) + sorted(TRACE_WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default=None, choices=["fullstack", "shortstack", "ref_t1", "ref_t2"],
+                    help="override the workload's traversal mode")
     args = ap.parse_args()
     if args.workload in TRACE_WORKLOADS:
         run_trace_workload(args)
@@ -362,6 +364,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = max(args.warmup, 3); K = args.steps; S = args.spp_per_step
     sc, params, desc = load_scene(args.workload)
+    mode_name = args.mode or WORKLOADS[args.workload][3]
+    params.mode = kdpt.MODES[mode_name]
     w, h = (int(x) for x in sc.camera['resolution'][0])
     npix = w * h
 
@@ -468,7 +472,7 @@ def main():
             traffic, traffic_kernel = measured_traffic(args.workload)
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_of": traffic_kernel,
-                    "kernel": "bounceKernel<%s>" % WORKLOADS[args.workload][3], "avg_launch_ms": launch_ms,
+                    "kernel": "bounceKernel<%s>" % mode_name, "avg_launch_ms": launch_ms,
                     "kernel_share_of_step": st["intersect_ms"] / st["total_ms"],
                     "algorithmic_bytes_per_ray_bounce": ab["bytes_per_ray_bounce"], "V_nodes_per_ray": ab["V"], "T_tris_per_ray": ab["T"],
                     "peak_source": peak_src,
@@ -490,7 +494,7 @@ def main():
                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": desc, "spp_per_step": S, "resolution": [w, h], "trace_depth": sc.trace_depth,
-                          "traversal": WORKLOADS[args.workload][3], "parallelism": f"sample-sharded x{world}, tree replicated, "
+                          "traversal": mode_name, "parallelism": f"sample-sharded x{world}, tree replicated, "
                           "NCCL all-reduce of the radiance buffer per step" if world > 1 else "single GPU",
                           "l2": "flushed between timed steps (256 MiB fill, untimed)"},
                "spp_per_s": S * world * K / (ms * 1e-3),

@@ -190,21 +190,27 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     if (S.numMaterials && (e = cudaMemcpyAsync(S.materials.p, scene->materials, sizeof(kdpt_material) * (size_t)S.numMaterials, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload materials"));
     if (S.numShapes && (e = cudaMemcpyAsync(S.offsets.p, scene->objMaterialOffsets, sizeof(int) * (size_t)S.numShapes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload offsets"));
     {
-        // World-space bounding sphere of every analytic geom (unit cube / radius-0.5 sphere under `transform`), inflated:
-        // a ray whose line passes farther than the radius from the centre provably misses the geom, so the kernel can
-        // skip the exact (and expensive) object-space test without changing any result.
-        std::vector<float> gb(4 * (size_t)(S.numGeoms > 0 ? S.numGeoms : 1), 0.f);
+        // World-space AABB of every analytic geom (the unit cube under `transform`; it also contains the radius-0.5
+        // sphere), padded: a ray that misses the padded box provably misses the geom, so the kernel can skip the exact
+        // (and expensive) object-space test without changing any result. Two float4 per geom: (lo, -), (hi, -).
+        std::vector<float> gb(8 * (size_t)(S.numGeoms > 0 ? S.numGeoms : 1), 0.f);
         for (int g = 0; g < S.numGeoms; g++) {
             const float* m = scene->geoms[g].transform;
-            double c0 = sqrt((double)m[0] * m[0] + (double)m[1] * m[1] + (double)m[2] * m[2]);
-            double c1 = sqrt((double)m[4] * m[4] + (double)m[5] * m[5] + (double)m[6] * m[6]);
-            double c2 = sqrt((double)m[8] * m[8] + (double)m[9] * m[9] + (double)m[10] * m[10]);
-            double r = scene->geoms[g].type == 1 ? 0.5 * (c0 + c1 + c2) : 0.5 * sqrt(c0 * c0 + c1 * c1 + c2 * c2);
-            double cmax = fabs((double)m[12]) > fabs((double)m[13]) ? fabs((double)m[12]) : fabs((double)m[13]);
-            if (fabs((double)m[14]) > cmax) cmax = fabs((double)m[14]);
-            r = r * 1.001 + 1e-3 + 1e-5 * cmax;
-            if (!(r == r) || !(r < 1e30)) r = INFINITY;     // degenerate transform: never cull
-            gb[4 * g] = m[12]; gb[4 * g + 1] = m[13]; gb[4 * g + 2] = m[14]; gb[4 * g + 3] = (float)r;
+            double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            bool bad = false;
+            for (int c = 0; c < 8; c++) {
+                double x = (c & 1) ? 0.5 : -0.5, y = (c & 2) ? 0.5 : -0.5, z = (c & 4) ? 0.5 : -0.5;
+                for (int a = 0; a < 3; a++) {
+                    double v = (double)m[a] * x + (double)m[4 + a] * y + (double)m[8 + a] * z + (double)m[12 + a];
+                    if (!(v == v) || !(fabs(v) < 1e30)) bad = true;
+                    lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a];
+                }
+            }
+            for (int a = 0; a < 3; a++) {
+                double pad = 2e-3 + 1e-4 * (hi[a] - lo[a]) + 1e-5 * (fabs(lo[a]) > fabs(hi[a]) ? fabs(lo[a]) : fabs(hi[a]));
+                gb[8 * g + a] = bad ? -INFINITY : (float)(lo[a] - pad);         // degenerate transform: never cull
+                gb[8 * g + 4 + a] = bad ? INFINITY : (float)(hi[a] + pad);
+            }
         }
         if ((rc = S.geomBounds.alloc(sizeof(float) * gb.size()))) return fail(rc);
         if ((e = cudaMemcpyAsync(S.geomBounds.p, gb.data(), sizeof(float) * gb.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload geom bounds"));

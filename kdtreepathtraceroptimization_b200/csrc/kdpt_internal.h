@@ -28,7 +28,7 @@ struct DeviceBuffer {
 
 // device copies of the analytic scene (render loop)
 struct SceneDev {
-    DeviceBuffer geoms, materials, offsets, geomBounds;   // geomBounds: float4 (centre, radius) per geom
+    DeviceBuffer geoms, materials, offsets, geomBounds;   // geomBounds: two float4 (padded world AABB lo, hi) per geom
     int numGeoms = 0, numMaterials = 0, numShapes = 0;
     kdpt_camera camera{};
     int traceDepth = 0;

@@ -202,7 +202,7 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
              const GenArgs gen)
 {
     __shared__ kdpt_geom sGeoms[kMaxSmemGeoms];
-    __shared__ float4 sBounds[kMaxSmemGeoms];
+    __shared__ float4 sBounds[2 * kMaxSmemGeoms];
     __shared__ int pk[kMaxBatch + 1];
     // per-thread values that phase C needs but the traversal (phase B) does not: parked in shared memory (word-major,
     // conflict free) so that the traversal runs with ~14 fewer live registers
@@ -212,7 +212,7 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         const unsigned* src = reinterpret_cast<const unsigned*>(S.geoms);
         unsigned* dst = reinterpret_cast<unsigned*>(sGeoms);
         for (int k = threadIdx.x; k < ng * (int)(sizeof(kdpt_geom) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
-        for (int k = threadIdx.x; k < ng; k += blockDim.x) sBounds[k] = __ldg(S.geomBounds + k);
+        for (int k = threadIdx.x; k < 2 * ng; k += blockDim.x) sBounds[k] = __ldg(S.geomBounds + k);
     }
     buildPacketPrefix(pk, st, bt.B, A.depth, kTicketPackets);
     const unsigned lane = threadIdx.x & 31u;
@@ -255,16 +255,21 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         }
         const bool doIsect = live && (A.stages & KDPT_STAGE_INTERSECT);
         if (doIsect) {
-            const float dd = dot(r.d, r.d);
+            const float dlen = length(r.d);
+            const V3 ginv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
             for (int g = 0; g < S.numGeoms; g++) {
-                // bounding-sphere filter (see kdpt_create): skip geoms the ray provably misses, that lie behind the
-                // origin, or whose nearest point is beyond the closest hit so far. The reference's result is the
-                // minimum over geoms of a distance that is -1 for exactly those, so nothing changes. NaN -> no skip.
-                const float4 bs = g < ng ? sBounds[g] : __ldg(S.geomBounds + g);
-                const V3 oc = mk(bs.x - r.o.x, bs.y - r.o.y, bs.z - r.o.z);
-                const float oc2 = dot(oc, oc), b = dot(oc, r.d), r2 = bs.w * bs.w;
-                if (oc2 > r2 && (b < 0.0f || oc2 * dd - b * b > r2 * dd * 1.0001f)) continue;
-                if (oc2 > r2 && tMin < FLT_MAX) { float nearest = sqrtf(oc2) - bs.w; if (nearest > tMin * 1.0001f + 1e-3f) continue; }
+                // world-AABB filter (see kdpt_create): skip geoms whose padded box the ray misses, that lie behind the
+                // origin, or whose box begins beyond the closest hit so far. The reference's result is the minimum over
+                // geoms of a distance that is -1 for exactly those, so nothing changes. Any NaN -> no skip.
+                const float4 blo = g < ng ? sBounds[2 * g] : __ldg(S.geomBounds + 2 * g);
+                const float4 bhi = g < ng ? sBounds[2 * g + 1] : __ldg(S.geomBounds + 2 * g + 1);
+                const float v1 = (blo.x - r.o.x) * ginv.x, v2 = (bhi.x - r.o.x) * ginv.x;
+                const float v3 = (blo.y - r.o.y) * ginv.y, v4 = (bhi.y - r.o.y) * ginv.y;
+                const float v5 = (blo.z - r.o.z) * ginv.z, v6 = (bhi.z - r.o.z) * ginv.z;
+                const float tn = fmaxf(fmaxf(fminf(v1, v2), fminf(v3, v4)), fminf(v5, v6));
+                const float tf = fminf(fminf(fmaxf(v1, v2), fmaxf(v3, v4)), fmaxf(v5, v6));
+                if (tn > tf || tf < 0.0f) continue;
+                if (tMin < FLT_MAX && tn * dlen > tMin * 1.0001f + 1e-3f) continue;
                 V3 pt, nr;
                 float tg = g < ng ? geomTest(sGeoms[g], r.o, r.d, pt, nr) : geomTest(S.geoms[g], r.o, r.d, pt, nr);
                 if (tg > 0.0f && tMin > tg) { tMin = tg; hitGeom = g; ipoint = pt; normal = nr; }
@@ -745,9 +750,9 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     if ((rc = ensureImage(ctx))) return rc;
     const kdpt_params& p = *params;
     const int n = ctx->pixelCount;
-    // iterations per launch: bounded by kMaxBatch and by ~1.5 GB of path state
+    // iterations per launch: bounded by kMaxBatch and by 8 GB of path state (of 180 GB)
     int maxBatch = kMaxBatch;
-    while (maxBatch > 1 && (size_t)maxBatch * n * 128 > ((size_t)3 << 29)) maxBatch >>= 1;
+    while (maxBatch > 1 && (size_t)maxBatch * n * 128 > ((size_t)8 << 30)) maxBatch >>= 1;
     if (iter_count < maxBatch) maxBatch = iter_count > 0 ? iter_count : 1;
     RenderBuffers rb;
     if ((rc = ensureRenderBuffers(ctx, n, maxBatch, rb, true))) return rc;
