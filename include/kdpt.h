@@ -102,7 +102,10 @@ typedef struct {
     int sortByMaterial;     /* 0 never, 1 only in iteration 2 (reference, pathtrace.cu:2600), 2 every bounce */
     int testingmode;        /* TESTINGMODE (pathtrace.cu:2478-2481, 2565-2574): time every intersect kernel with CUDA
                                events and report the sum in kdpt_render_stats.intersectMs */
-    int reserved[3];
+    int laneQueue;          /* tuning, no effect on results: how a bounce traverses the lanes of a 32-path packet that enter
+                               the KD tree. 0 = the kernel decides per launch from the measured entering fraction
+                               (default), 1 = always at once, 2 = always pooled in the per-warp queue */
+    int reserved[2];
 } kdpt_params;
 
 typedef struct {            /* filled by kdpt_render */

@@ -62,7 +62,7 @@ class CParams(ctypes.Structure):
     _fields_ = [("focalLength", ctypes.c_float), ("dofAngle", ctypes.c_float), ("softness", ctypes.c_float),
                 ("antialias", ctypes.c_int), ("enableSss", ctypes.c_int), ("compaction", ctypes.c_int),
                 ("mode", ctypes.c_int), ("sortByMaterial", ctypes.c_int), ("testingmode", ctypes.c_int),
-                ("reserved", ctypes.c_int * 3)]
+                ("laneQueue", ctypes.c_int), ("reserved", ctypes.c_int * 2)]
 
 
 class CRenderStats(ctypes.Structure):

@@ -50,6 +50,11 @@ struct LoopState {
     int np[kMaxBatch][kMaxBounces + 2];      // live paths of each batched iteration at the start of each bounce
     unsigned ticket[2 * (kMaxBounces + 1)];  // packet counters: [b] bounce kernel, [9+b] compaction
     unsigned long long bounceRays[kMaxBounces];
+    unsigned long long travRays[kMaxBounces];   // of those, rays that entered the KD tree's root box
+    // entering fraction per bounce depth of the most recent batch (< 0: not measured yet) and the counter values it
+    // was taken at; maintained by scanPacketsKernel
+    unsigned long long seenRays[kMaxBounces], seenTrav[kMaxBounces];
+    float enterFrac[kMaxBounces];
 };
 
 // A batch = B consecutive iterations of this rank, each owning one segment of `cap` path slots (and capPackets packet
@@ -88,6 +93,7 @@ struct BounceArgs {
     int iter, depth, stages;    // stages: kdpt_stage bits; 4 = gather finished paths into the image (compaction on)
     float softness; int enableSss;
     float eps;
+    int queuePolicy;            // 0 direct, 1 queued, 2 decided by the kernel (see bounceKernel)
 };
 
 __host__ __device__ inline unsigned hUtilhash(unsigned a)
@@ -195,6 +201,300 @@ struct GenArgs { kdpt_camera cam; IterConsts ics; int traceDepth; float focal; }
 #ifndef KDPT_BOUNCE_MIN_BLOCKS
 #define KDPT_BOUNCE_MIN_BLOCKS(MODE) ((MODE) == KDPT_SHORTSTACK ? 4 : 5)
 #endif
+// Everything phase C needs about one path (also the record of the per-warp deferred-traversal queue).
+struct PathWork {
+    PathRay r; float4 cp; int2 bm;
+    float tMin; int hitGeom; V3 ipoint, normal;
+    int seg, i, packet;        // iteration segment, path index inside it, packet index inside the segment
+};
+constexpr int kWorkWords = 23;
+constexpr int kParkWords = 14;      // the part of it the direct (unqueued) variant parks during the traversal
+#ifndef KDPT_DENSE_PACKET
+#define KDPT_DENSE_PACKET 16
+#endif
+constexpr int kDensePacket = KDPT_DENSE_PACKET;   // a packet with at least this many lanes inside the root box is traversed at once
+
+// ---- phase C for one path: scatter, shade, gather, write back. Returns whether the path survives. ----
+template <int MODE>
+__device__ __forceinline__ bool finishPath(PathWork& w, const Hit& H, bool doIsect, const Tree& T, const SceneView& S,
+                                           const PathSoA& P, const BounceArgs& A, const Batch& bt, float* __restrict__ accum,
+                                           const unsigned* packetAlive, kdpt_intersection* __restrict__ isectOut)
+{
+    const size_t slot = (size_t)w.seg * bt.cap + w.i;
+    int remaining = w.bm.x;
+    V3 color = mk(w.cp.x, w.cp.y, w.cp.z);
+    float t = 0.0f; int matId = 0;      // dev_intersections is memset to 0 per bounce (pathtrace.cu:2473)
+    if (doIsect) {
+        bool objHit = H.tri >= 0;
+        if (objHit) {
+            // the reference's nudged point: o + d*z + n*eps (pathtrace.cu:993-995)
+            w.normal = mk(H.nx, H.ny, H.nz);
+            w.ipoint = (w.r.o + w.r.d * H.z) + w.normal * A.eps;
+            w.tMin = H.t;
+            // reference: material of the LAST triangle glm accepted (pathtrace.cu:991); exact modes: of the hit
+            int mtl = (MODE == KDPT_REF_T1 || MODE == KDPT_REF_T2) ? H.anyMtl : H.mtl;
+            matId = mtl + T.materialSize - 1;
+        } else if (w.hitGeom >= 0) matId = S.geoms[w.hitGeom].materialid;
+        // multi-shape OBJs index past materials[] in the reference (Appendix A #5); stay in bounds here
+        matId = matId < 0 ? 0 : (matId >= S.numMaterials ? S.numMaterials - 1 : matId);
+        if (!objHit && w.hitGeom < 0) t = -1.0f;          // pathtrace.cu:1683-1686
+        else {
+            const kdpt_material m = S.materials[matId];
+            const int iter = bt.iterBase + w.seg * bt.iterStride;
+            scatterRay(w.r, w.ipoint, w.normal, m, pathSeed(iter, w.i, A.depth), A.softness);
+            t = w.tMin;
+            w.bm.y = matId;
+        }
+        if (isectOut) {
+            kdpt_intersection is; is.t = t; is.surfaceNormal[0] = t == -1.0f ? 0.f : w.normal.x;
+            is.surfaceNormal[1] = t == -1.0f ? 0.f : w.normal.y; is.surfaceNormal[2] = t == -1.0f ? 0.f : w.normal.z;
+            is.materialId = t == -1.0f ? 0 : matId;
+            isectOut[slot] = is;
+        }
+    } else if (isectOut) {      // shade-only call: the caller supplies the intersections
+        kdpt_intersection is = isectOut[slot];
+        t = is.t; matId = is.materialId;
+    }
+    if (A.stages & KDPT_STAGE_SHADE) {
+        if (t > 0.0f) remaining = shadeHit(S.materials[matId], A.enableSss != 0, w.r.sdepth, color, remaining);
+        else { color = mk(0, 0, 0); remaining = 0; }
+    }
+    if ((A.stages & 4) && remaining == 0) {     // partialGather: each pixel's path finishes exactly once per iteration
+        float* px = accum + 3 * ((size_t)w.seg * bt.npix + __float_as_int(w.cp.w));
+        px[0] = color.x; px[1] = color.y; px[2] = color.z;
+    }
+    const bool alive = remaining > 0;
+    if ((A.stages & 8) && alive && accum) {     // last bounce of the loop: a path still alive is never gathered
+        float* px = accum + 3 * ((size_t)w.seg * bt.npix + __float_as_int(w.cp.w));
+        px[0] = 0.f; px[1] = 0.f; px[2] = 0.f;
+    }
+    // with compaction on, a finished path is never looked at again (its radiance went to accum above and the
+    // compaction reads the packet's alive mask, not the path): only survivors are written back
+    if (alive || !packetAlive) {
+        P.od[slot] = make_float4(w.r.o.x, w.r.o.y, w.r.o.z, w.r.sdepth);
+        P.dr[slot] = make_float4(w.r.d.x, w.r.d.y, w.r.d.z, w.r.inside ? 1.0f : 0.0f);
+        P.cp[slot] = make_float4(color.x, color.y, color.z, w.cp.w);
+        w.bm.x = remaining;
+        P.bm[slot] = w.bm;
+    }
+    return alive;
+}
+
+// One bounce over all live paths of the batch. QUEUE selects how the lanes of a packet that enter the KD tree are
+// traversed:
+//  QUEUE: they are parked in a per-warp ring in shared memory (word-major, conflict free) and the warp traverses when 32
+//    have accumulated, with every lane busy; all other lanes of the packet finish immediately. When only a few lanes of a
+//    packet enter the tree (the mesh covers a small part of the scene), traversing right away would run the whole
+//    traversal with 1-3 of 32 lanes active (measured: a third of all issue slots on the cornell scenes). A deferred path
+//    reports its survival to the packet's compaction bookkeeping with atomics afterwards. A packet that is mostly inside
+//    the box is flushed right away, so that its rays are traversed together instead of being mixed with strangers.
+//  !QUEUE: every packet is traversed at once by the lanes that need it; the same array only parks what phase C needs but
+//    the traversal does not (column = lane), so that the traversal runs with ~14 fewer live registers. Better when a
+//    third or more of the lanes enter the tree anyway (measured: the queue's bookkeeping and the loss of coherence then
+//    cost more than the idle lanes). The kernel picks per launch from the entering fraction it measured at this bounce
+//    depth in the previous batch (LoopState::enterFrac), see bounceKernel.
+template <int MODE, bool GEN, bool QUEUE>
+__device__ __forceinline__ void
+bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, const BounceArgs& A, const Batch& bt,
+           float* __restrict__ accum, int* __restrict__ packetCount, unsigned* __restrict__ packetAlive,
+           kdpt_intersection* __restrict__ isectOut, const GenArgs& gen,
+           const kdpt_geom* sGeoms, const float4* sBounds, const int* pk, float* sDefRaw, int ng)
+{
+    constexpr int kSlots = QUEUE ? 64 : 32;
+    constexpr int kWords = QUEUE ? kWorkWords : kParkWords;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    float (*def)[kSlots] = reinterpret_cast<float (*)[kSlots]>(sDefRaw + (threadIdx.x >> 5) * (kWords * kSlots));
+    unsigned long long liveLocal = 0, travLocal = 0;
+    int segHint = 0;
+    int qHead = 0, defCount = 0;            // warp-uniform: ring start and fill
+    const int totalTickets = pk[bt.B];
+    bool finished = false, flushWanted = false;
+    for (;;) {
+        // One pass of this loop either drains up to 32 queued paths (QUEUE only: phase B + C, one path per lane, every
+        // lane busy; when 32 are waiting, after a dense packet, and at the end until the queue is empty) or takes a new
+        // packet (phase A; then QUEUE parks the lanes that enter the tree and finishes the others, !QUEUE traverses at
+        // once). Both feed the single phase-C call at the bottom.
+        PathWork w;
+        w.bm = make_int2(0, 0); w.cp = make_float4(0, 0, 0, 0);
+        w.r.o = mk(0, 0, 0); w.r.d = mk(0, 0, 0); w.r.inside = false; w.r.sdepth = 0.f;
+        w.tMin = FLT_MAX; w.hitGeom = -1; w.ipoint = mk(0, 0, 0); w.normal = mk(0, 0, 0);
+        w.seg = 0; w.i = 0; w.packet = 0;
+        Hit H;
+        bool finishNow = false, doIsect = false;
+        const bool drain = QUEUE && (defCount >= 32 || (flushWanted && defCount > 0));
+        bool alive = false, live = false;
+        unsigned defMask = 0;
+        if (drain) {
+            const int nq = defCount < 32 ? defCount : 32;
+            const bool have = (int)lane < nq;
+            const int e = (qHead + (int)lane) & (kSlots - 1);
+            if (have) {
+                w.r.o = mk(def[0][e], def[1][e], def[2][e]); w.r.d = mk(def[3][e], def[4][e], def[5][e]);
+                w.tMin = def[6][e];
+            }
+            initHit(H, w.tMin);
+            if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, have, w.r.o, w.r.d, w.tMin, 0.00001f, H);
+            else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, have, w.r.o, w.r.d, w.tMin, 0.0001f, H);
+            else if (have) {
+                if (MODE == KDPT_REF_T1) traceRef<false>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
+                else traceRef<true>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
+            }
+            if (have) {
+                w.r.inside = def[7][e] != 0.0f; w.r.sdepth = def[8][e];
+                w.cp = make_float4(def[9][e], def[10][e], def[11][e], def[12][e]);
+                w.bm = make_int2(__float_as_int(def[13][e]), __float_as_int(def[14][e]));
+                w.hitGeom = __float_as_int(def[15][e]);
+                w.ipoint = mk(def[16][e], def[17][e], def[18][e]); w.normal = mk(def[19][e], def[20][e], def[21][e]);
+                const int segi = __float_as_int(def[22][e]);
+                w.seg = (int)((unsigned)segi >> 27); w.i = segi & 0x7ffffff; w.packet = w.i >> 5;
+            }
+            finishNow = have; doIsect = true;
+            qHead = (qHead + nq) & (kSlots - 1);
+            defCount -= nq;
+            flushWanted = false;
+        } else {
+            if (finished) {
+                if (defCount == 0) break;
+                flushWanted = true;
+                continue;
+            }
+            int ticket = 0;
+            if (lane == 0) ticket = (int)atomicAdd(&st->ticket[A.depth], 1u);
+            ticket = __shfl_sync(FULL, ticket, 0);
+            if (ticket >= totalTickets) { finished = true; continue; }
+            // ---- phase A (per lane): load the path, test the analytic geoms ----
+            float4 od = make_float4(0, 0, 0, 0), dr = od;
+            bool inRange = false, needTrav = false;
+            while (segHint + 1 < bt.B && ticket >= pk[segHint + 1]) segHint++;     // a warp's tickets only grow
+            const int seg = segHint;
+            const int n = st->np[seg][A.depth];
+            const int packet = ticket - pk[seg];
+            const unsigned i = (unsigned)packet * 32u + lane;                  // path index inside its iteration
+            w.seg = seg; w.i = (int)i; w.packet = packet;
+            inRange = i < (unsigned)n;
+            if (inRange) {
+                const size_t slot = (size_t)seg * bt.cap + i;
+                if (GEN) {          // first bounce: path i of an iteration is pixel i; nothing to read
+                    V3 org, dir;
+                    primaryRay(gen.cam, gen.ics.c[seg], (int)i, gen.focal, org, dir);
+                    od = make_float4(org.x, org.y, org.z, 0.0f); dr = make_float4(dir.x, dir.y, dir.z, 0.0f);
+                    w.cp = make_float4(1.0f, 1.0f, 1.0f, __int_as_float((int)i)); w.bm = make_int2(gen.traceDepth, 0);
+                } else {
+                    w.bm = P.bm[slot]; od = P.od[slot]; dr = P.dr[slot]; w.cp = P.cp[slot];     // four independent loads, one round trip
+                }
+                if (w.bm.x > 0) {
+                    live = true;
+                    w.r.o = mk(od.x, od.y, od.z); w.r.d = mk(dr.x, dr.y, dr.z); w.r.inside = dr.w != 0.0f; w.r.sdepth = od.w;
+                }
+            }
+            doIsect = live && (A.stages & KDPT_STAGE_INTERSECT);
+            if (doIsect) {
+                const float dlen = length(w.r.d);
+                const V3 ginv = mk(1.0f / w.r.d.x, 1.0f / w.r.d.y, 1.0f / w.r.d.z);
+                for (int g = 0; g < S.numGeoms; g++) {
+                    // world-AABB filter (see kdpt_create): skip geoms whose padded box the ray misses, that lie behind
+                    // the origin, or whose box begins beyond the closest hit so far. The reference's result is the
+                    // minimum over geoms of a distance that is -1 for exactly those, so nothing changes. NaN -> no skip.
+                    const float4 blo = g < ng ? sBounds[2 * g] : __ldg(S.geomBounds + 2 * g);
+                    const float4 bhi = g < ng ? sBounds[2 * g + 1] : __ldg(S.geomBounds + 2 * g + 1);
+                    const float v1 = (blo.x - w.r.o.x) * ginv.x, v2 = (bhi.x - w.r.o.x) * ginv.x;
+                    const float v3 = (blo.y - w.r.o.y) * ginv.y, v4 = (bhi.y - w.r.o.y) * ginv.y;
+                    const float v5 = (blo.z - w.r.o.z) * ginv.z, v6 = (bhi.z - w.r.o.z) * ginv.z;
+                    const float tn = fmaxf(fmaxf(fminf(v1, v2), fminf(v3, v4)), fminf(v5, v6));
+                    const float tf = fminf(fminf(fmaxf(v1, v2), fmaxf(v3, v4)), fmaxf(v5, v6));
+                    if (tn > tf || tf < 0.0f) continue;
+                    if (w.tMin < FLT_MAX && tn * dlen > w.tMin * 1.0001f + 1e-3f) continue;
+                    V3 pt, nr;
+                    float tg = g < ng ? geomTest(sGeoms[g], w.r.o, w.r.d, pt, nr) : geomTest(S.geoms[g], w.r.o, w.r.d, pt, nr);
+                    if (tg > 0.0f && w.tMin > tg) { w.tMin = tg; w.hitGeom = g; w.ipoint = pt; w.normal = nr; }
+                }
+                // does the ray reach the tree at all? (the traversals' own first step: a miss of the root box ends them)
+                if (T.numNodes != 0) {
+                    float t0, t1;
+                    needTrav = slab(w.r.o, ginv, T.rootLo, T.rootHi, t0, t1);
+                    // exact modes: also done when the box begins beyond the closest geom hit (the kernels' early-exit rule)
+                    if ((MODE == KDPT_FULLSTACK || MODE == KDPT_SHORTSTACK) && needTrav && w.tMin < FLT_MAX && dlen > 0.0f &&
+                        t0 > w.tMin / dlen + kExitSlack / dlen) needTrav = false;
+                }
+            }
+            defMask = __ballot_sync(FULL, needTrav);
+            initHit(H, w.tMin);
+            if (QUEUE) {
+                // lanes whose ray enters the tree go to the queue (fewer than 32 are waiting there), the others finish now
+                if (needTrav) {
+                    const int e = (qHead + defCount + __popc(defMask & ((1u << lane) - 1u))) & (kSlots - 1);
+                    def[0][e] = w.r.o.x; def[1][e] = w.r.o.y; def[2][e] = w.r.o.z;
+                    def[3][e] = w.r.d.x; def[4][e] = w.r.d.y; def[5][e] = w.r.d.z; def[6][e] = w.tMin;
+                    def[7][e] = w.r.inside ? 1.0f : 0.0f; def[8][e] = w.r.sdepth;
+                    def[9][e] = w.cp.x; def[10][e] = w.cp.y; def[11][e] = w.cp.z; def[12][e] = w.cp.w;
+                    def[13][e] = __int_as_float(w.bm.x); def[14][e] = __int_as_float(w.bm.y);
+                    def[15][e] = __int_as_float(w.hitGeom);
+                    def[16][e] = w.ipoint.x; def[17][e] = w.ipoint.y; def[18][e] = w.ipoint.z;
+                    def[19][e] = w.normal.x; def[20][e] = w.normal.y; def[21][e] = w.normal.z;
+                    def[22][e] = __int_as_float((w.seg << 27) | w.i);
+                }
+                defCount += __popc(defMask);
+                // camera rays (first bounce) are coherent: a packet's rays that reach the mesh are traversed together at
+                // once; later bounces are incoherent and are pooled unless most of the packet is in the box anyway
+                if (__popc(defMask) >= (GEN ? 1 : kDensePacket)) flushWanted = true;
+                finishNow = live && !needTrav;
+            } else {
+                if (defMask) {      // ---- phase B (whole warp): KD traversal + triangle tests for the lanes that need it
+                    def[0][lane] = w.cp.x; def[1][lane] = w.cp.y; def[2][lane] = w.cp.z; def[3][lane] = w.cp.w;
+                    def[4][lane] = __int_as_float(w.bm.x); def[5][lane] = __int_as_float(w.bm.y); def[6][lane] = w.r.sdepth;
+                    def[7][lane] = __int_as_float(w.hitGeom);
+                    def[8][lane] = w.ipoint.x; def[9][lane] = w.ipoint.y; def[10][lane] = w.ipoint.z;
+                    def[11][lane] = w.normal.x; def[12][lane] = w.normal.y; def[13][lane] = w.normal.z;
+                    if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.00001f, H);
+                    else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.0001f, H);
+                    else if (needTrav) {
+                        if (MODE == KDPT_REF_T1) traceRef<false>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
+                        else traceRef<true>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
+                    }
+                    w.cp = make_float4(def[0][lane], def[1][lane], def[2][lane], def[3][lane]);
+                    w.bm = make_int2(__float_as_int(def[4][lane]), __float_as_int(def[5][lane])); w.r.sdepth = def[6][lane];
+                    w.hitGeom = __float_as_int(def[7][lane]);
+                    w.ipoint = mk(def[8][lane], def[9][lane], def[10][lane]); w.normal = mk(def[11][lane], def[12][lane], def[13][lane]);
+                }
+                finishNow = live;
+            }
+            if (!live && inRange) {
+                alive = w.bm.x > 0;
+                if (GEN) { const size_t slot = (size_t)w.seg * bt.cap + w.i; P.od[slot] = od; P.dr[slot] = dr; P.cp[slot] = w.cp; P.bm[slot] = w.bm; }     // traceDepth <= 0
+            }
+        }
+        // ---- phase C (per lane): scatter, shade, gather, write back ----
+        if (finishNow) alive = finishPath<MODE>(w, H, doIsect, T, S, P, A, bt, accum, packetAlive, isectOut);
+        if (drain) {
+            // a drained path adds itself to its packet's compaction entry, which was stored when the packet was taken
+            // (ordered by the __syncwarp that ended that pass)
+            if (alive) {
+                if (packetCount) atomicAdd(&packetCount[w.seg * bt.capPackets + w.packet], 1);
+                if (packetAlive) atomicOr(&packetAlive[w.seg * bt.capPackets + w.packet], 1u << (w.i & 31));
+            }
+        } else {
+            const unsigned aliveMask = __ballot_sync(FULL, alive);
+            const unsigned liveMask = __ballot_sync(FULL, live);
+            if (lane == 0) {
+                if (packetCount) packetCount[w.seg * bt.capPackets + w.packet] = __popc(aliveMask);
+                if (packetAlive) packetAlive[w.seg * bt.capPackets + w.packet] = aliveMask;
+                liveLocal += (unsigned)__popc(liveMask);
+                travLocal += (unsigned)__popc(defMask);
+            }
+        }
+        __syncwarp();       // queue slots read above may be refilled, and the packet entry is visible to later atomics
+    }
+    if (lane == 0 && liveLocal && A.depth < kMaxBounces) {
+        atomicAdd(&st->bounceRays[A.depth], liveLocal);
+        if (travLocal) atomicAdd(&st->travRays[A.depth], travLocal);
+    }
+}
+
+// entering fraction below which the queued variant is used
+#ifndef KDPT_QUEUE_BELOW
+#define KDPT_QUEUE_BELOW 0.30f
+#endif
 template <int MODE, bool GEN>
 __global__ void __launch_bounds__(kThreads, KDPT_BOUNCE_MIN_BLOCKS(MODE))
 bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch bt, float* __restrict__ accum,
@@ -204,9 +504,7 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
     __shared__ kdpt_geom sGeoms[kMaxSmemGeoms];
     __shared__ float4 sBounds[2 * kMaxSmemGeoms];
     __shared__ int pk[kMaxBatch + 1];
-    // per-thread values that phase C needs but the traversal (phase B) does not: parked in shared memory (word-major,
-    // conflict free) so that the traversal runs with ~14 fewer live registers
-    __shared__ float sPark[14][kThreads];
+    __shared__ float sDef[(kThreads / 32) * (GEN ? kParkWords * 32 : kWorkWords * 64)];
     const int ng = S.numGeoms < kMaxSmemGeoms ? S.numGeoms : kMaxSmemGeoms;
     {
         const unsigned* src = reinterpret_cast<const unsigned*>(S.geoms);
@@ -215,161 +513,21 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
         for (int k = threadIdx.x; k < 2 * ng; k += blockDim.x) sBounds[k] = __ldg(S.geomBounds + k);
     }
     buildPacketPrefix(pk, st, bt.B, A.depth, kTicketPackets);
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long liveLocal = 0;
-    int segHint = 0;
-    for (;;) {
-        int ticket = 0;
-        if (lane == 0) ticket = (int)atomicAdd(&st->ticket[A.depth], 1u);
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket >= pk[bt.B]) break;
-        while (segHint + 1 < bt.B && ticket >= pk[segHint + 1]) segHint++;     // a warp's tickets only grow
-        const int seg = segHint;
-        const int n = st->np[seg][A.depth];
-        const int iter = bt.iterBase + seg * bt.iterStride;
-        const int numPackets = (n + 31) >> 5;
-      for (int q = 0; q < kTicketPackets; q++) {
-        const int packet = (ticket - pk[seg]) * kTicketPackets + q;
-        if (packet >= numPackets) break;
-        const unsigned i = (unsigned)packet * 32u + lane;                  // path index inside its iteration
-        const size_t slot = (size_t)seg * bt.cap + i;
-        bool alive = false, live = false;
-        // ---- phase A (per lane): load the path, test the analytic geoms ----
-        int2 bm = make_int2(0, 0);
-        float4 od = make_float4(0, 0, 0, 0), dr = od, cp = od;
-        PathRay r; r.o = mk(0, 0, 0); r.d = mk(0, 0, 0); r.inside = false; r.sdepth = 0.f;
-        float tMin = FLT_MAX; int hitGeom = -1; V3 ipoint = mk(0, 0, 0), normal = mk(0, 0, 0);
-        if (i < (unsigned)n) {
-            if (GEN) {          // first bounce: path i of an iteration is pixel i; nothing to read
-                V3 org, dir;
-                primaryRay(gen.cam, gen.ics.c[seg], (int)i, gen.focal, org, dir);
-                od = make_float4(org.x, org.y, org.z, 0.0f); dr = make_float4(dir.x, dir.y, dir.z, 0.0f);
-                cp = make_float4(1.0f, 1.0f, 1.0f, __int_as_float((int)i)); bm = make_int2(gen.traceDepth, 0);
-            } else {
-                bm = P.bm[slot]; od = P.od[slot]; dr = P.dr[slot]; cp = P.cp[slot];     // four independent loads, one round trip
-            }
-            if (bm.x > 0) {
-                live = true;
-                r.o = mk(od.x, od.y, od.z); r.d = mk(dr.x, dr.y, dr.z); r.inside = dr.w != 0.0f; r.sdepth = od.w;
-            }
-        }
-        const bool doIsect = live && (A.stages & KDPT_STAGE_INTERSECT);
-        if (doIsect) {
-            const float dlen = length(r.d);
-            const V3 ginv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-            for (int g = 0; g < S.numGeoms; g++) {
-                // world-AABB filter (see kdpt_create): skip geoms whose padded box the ray misses, that lie behind the
-                // origin, or whose box begins beyond the closest hit so far. The reference's result is the minimum over
-                // geoms of a distance that is -1 for exactly those, so nothing changes. Any NaN -> no skip.
-                const float4 blo = g < ng ? sBounds[2 * g] : __ldg(S.geomBounds + 2 * g);
-                const float4 bhi = g < ng ? sBounds[2 * g + 1] : __ldg(S.geomBounds + 2 * g + 1);
-                const float v1 = (blo.x - r.o.x) * ginv.x, v2 = (bhi.x - r.o.x) * ginv.x;
-                const float v3 = (blo.y - r.o.y) * ginv.y, v4 = (bhi.y - r.o.y) * ginv.y;
-                const float v5 = (blo.z - r.o.z) * ginv.z, v6 = (bhi.z - r.o.z) * ginv.z;
-                const float tn = fmaxf(fmaxf(fminf(v1, v2), fminf(v3, v4)), fminf(v5, v6));
-                const float tf = fminf(fminf(fmaxf(v1, v2), fmaxf(v3, v4)), fmaxf(v5, v6));
-                if (tn > tf || tf < 0.0f) continue;
-                if (tMin < FLT_MAX && tn * dlen > tMin * 1.0001f + 1e-3f) continue;
-                V3 pt, nr;
-                float tg = g < ng ? geomTest(sGeoms[g], r.o, r.d, pt, nr) : geomTest(S.geoms[g], r.o, r.d, pt, nr);
-                if (tg > 0.0f && tMin > tg) { tMin = tg; hitGeom = g; ipoint = pt; normal = nr; }
-            }
-        }
-        {
-            const int t = threadIdx.x;
-            sPark[0][t] = cp.x; sPark[1][t] = cp.y; sPark[2][t] = cp.z; sPark[3][t] = cp.w;
-            sPark[4][t] = __int_as_float(bm.x); sPark[5][t] = __int_as_float(bm.y); sPark[6][t] = r.sdepth;
-            sPark[7][t] = __int_as_float(hitGeom);
-            sPark[8][t] = ipoint.x; sPark[9][t] = ipoint.y; sPark[10][t] = ipoint.z;
-            sPark[11][t] = normal.x; sPark[12][t] = normal.y; sPark[13][t] = normal.z;
-        }
-        // ---- phase B (whole warp): KD traversal + triangle tests ----
-        Hit H;
-        if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, doIsect, r.o, r.d, tMin, 0.00001f, H);
-        else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, doIsect, r.o, r.d, tMin, 0.0001f, H);
-        else if (doIsect) {
-            if (MODE == KDPT_REF_T1) traceRef<false>(T, r.o, r.d, tMin, H, nullptr);
-            else traceRef<true>(T, r.o, r.d, tMin, H, nullptr);
-        }
-        // ---- phase C (per lane): scatter, shade, gather, write back ----
-        {
-            const int t = threadIdx.x;
-            cp = make_float4(sPark[0][t], sPark[1][t], sPark[2][t], sPark[3][t]);
-            bm = make_int2(__float_as_int(sPark[4][t]), __float_as_int(sPark[5][t])); r.sdepth = sPark[6][t];
-            hitGeom = __float_as_int(sPark[7][t]);
-            ipoint = mk(sPark[8][t], sPark[9][t], sPark[10][t]); normal = mk(sPark[11][t], sPark[12][t], sPark[13][t]);
-        }
-        if (live) {
-            int remaining = bm.x;
-            V3 color = mk(cp.x, cp.y, cp.z);
-            float t = 0.0f; int matId = 0;      // dev_intersections is memset to 0 per bounce (pathtrace.cu:2473)
-            if (doIsect) {
-                bool objHit = H.tri >= 0;
-                if (objHit) {
-                    // the reference's nudged point: o + d*z + n*eps (pathtrace.cu:993-995)
-                    normal = mk(H.nx, H.ny, H.nz);
-                    ipoint = (r.o + r.d * H.z) + normal * A.eps;
-                    tMin = H.t;
-                    // reference: material of the LAST triangle glm accepted (pathtrace.cu:991); exact modes: of the hit
-                    int mtl = (MODE == KDPT_REF_T1 || MODE == KDPT_REF_T2) ? H.anyMtl : H.mtl;
-                    matId = mtl + T.materialSize - 1;
-                } else if (hitGeom >= 0) matId = S.geoms[hitGeom].materialid;
-                // multi-shape OBJs index past materials[] in the reference (Appendix A #5); stay in bounds here
-                matId = matId < 0 ? 0 : (matId >= S.numMaterials ? S.numMaterials - 1 : matId);
-                if (!objHit && hitGeom < 0) t = -1.0f;          // pathtrace.cu:1683-1686
-                else {
-                    const kdpt_material m = S.materials[matId];
-                    scatterRay(r, ipoint, normal, m, pathSeed(iter, (int)i, A.depth), A.softness);
-                    t = tMin;
-                    bm.y = matId;
-                }
-                if (isectOut) {
-                    kdpt_intersection is; is.t = t; is.surfaceNormal[0] = t == -1.0f ? 0.f : normal.x;
-                    is.surfaceNormal[1] = t == -1.0f ? 0.f : normal.y; is.surfaceNormal[2] = t == -1.0f ? 0.f : normal.z;
-                    is.materialId = t == -1.0f ? 0 : matId;
-                    isectOut[slot] = is;
-                }
-            } else if (isectOut) {      // shade-only call: the caller supplies the intersections
-                kdpt_intersection is = isectOut[slot];
-                t = is.t; matId = is.materialId;
-            }
-            if (A.stages & KDPT_STAGE_SHADE) {
-                if (t > 0.0f) remaining = shadeHit(S.materials[matId], A.enableSss != 0, r.sdepth, color, remaining);
-                else { color = mk(0, 0, 0); remaining = 0; }
-            }
-            if ((A.stages & 4) && remaining == 0) {     // partialGather: each pixel's path finishes exactly once per iteration
-                int pix = __float_as_int(cp.w);
-                float* px = accum + 3 * ((size_t)seg * bt.npix + pix);
-                px[0] = color.x; px[1] = color.y; px[2] = color.z;
-            }
-            alive = remaining > 0;
-            if ((A.stages & 8) && alive && accum) {     // last bounce of the loop: a path still alive is never gathered
-                float* px = accum + 3 * ((size_t)seg * bt.npix + __float_as_int(cp.w));
-                px[0] = 0.f; px[1] = 0.f; px[2] = 0.f;
-            }
-            // with compaction on, a finished path is never looked at again (its radiance went to accum above and the
-            // compaction reads the packet's alive mask, not the path): only survivors are written back
-            if (alive || !packetAlive) {
-                P.od[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.sdepth);
-                P.dr[slot] = make_float4(r.d.x, r.d.y, r.d.z, r.inside ? 1.0f : 0.0f);
-                P.cp[slot] = make_float4(color.x, color.y, color.z, cp.w);
-                bm.x = remaining;
-                P.bm[slot] = bm;
-            }
-        } else if (i < (unsigned)n) {
-            alive = bm.x > 0;
-            if (GEN) { P.od[slot] = od; P.dr[slot] = dr; P.cp[slot] = cp; P.bm[slot] = bm; }     // traceDepth <= 0
-        }
-        unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
-        unsigned liveMask = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) {
-            if (packetCount) packetCount[seg * bt.capPackets + packet] = __popc(aliveMask);
-            if (packetAlive) packetAlive[seg * bt.capPackets + packet] = aliveMask;
-            liveLocal += (unsigned)__popc(liveMask);
-        }
-      }
+    // Camera rays are coherent and are always traversed directly. Later bounces: the fraction of rays that entered the
+    // tree at this depth in the previous batch (stable from batch to batch; written by scanPacketsKernel), or, in a
+    // context's first batch, at the previous depth of this batch. Uniform over the grid: nothing writes these during
+    // the launch.
+    bool queue = false;
+    if (!GEN) {
+        if (A.queuePolicy == 2) {
+            float f = 1.0f;
+            if (st->enterFrac[A.depth] >= 0.0f) f = st->enterFrac[A.depth];
+            else if (A.depth > 1 && st->enterFrac[A.depth - 1] >= 0.0f) f = st->enterFrac[A.depth - 1];
+            queue = f < KDPT_QUEUE_BELOW;
+        } else queue = A.queuePolicy == 1;
     }
-    if (lane == 0 && liveLocal && A.depth < kMaxBounces) atomicAdd(&st->bounceRays[A.depth], liveLocal);
+    if (!GEN && queue) bounceBody<MODE, false, true>(T, S, P, st, A, bt, accum, packetCount, packetAlive, isectOut, gen, sGeoms, sBounds, pk, sDef, ng);
+    else bounceBody<MODE, GEN, false>(T, S, P, st, A, bt, accum, packetCount, packetAlive, isectOut, gen, sGeoms, sBounds, pk, sDef, ng);
 }
 
 // ---- stream compaction (replaces thrust::remove_if, pathtrace.cu:2591-2597) ---------------------------------------
@@ -383,6 +541,12 @@ scanPacketsKernel(int* __restrict__ packetCountAll, LoopState* st, int depth, in
     const int seg = blockIdx.x;                     // one block per batched iteration
     int* packetCount = packetCountAll + (size_t)seg * capPackets;
     const int n = st->np[seg][depth];
+    if (seg == 0 && threadIdx.x == 0 && depth < kMaxBounces) {      // entering fraction of the bounce that just ran
+        const unsigned long long r = st->bounceRays[depth], t = st->travRays[depth];
+        const unsigned long long dr = r - st->seenRays[depth];
+        if (dr) st->enterFrac[depth] = (float)(t - st->seenTrav[depth]) / (float)dr;
+        st->seenRays[depth] = r; st->seenTrav[depth] = t;
+    }
     if (!compaction) { if (threadIdx.x == 0) st->np[seg][depth + 1] = n; return; }
     const int numPackets = (n + 31) >> 5;
     if (threadIdx.x == 0) carry = 0;
@@ -599,7 +763,10 @@ static int ensureRenderBuffers(kdpt_ctx* ctx, int n, int batch, RenderBuffers& r
     carve(ctx->pathsA, rb.A); carve(ctx->pathsB, rb.B);
     bool fresh = ctx->scanTmp.p == nullptr;
     if ((rc = ctx->scanTmp.ensure(sizeof(LoopState)))) return rc;
-    if (fresh) KDPT_CUDA(cudaMemsetAsync(ctx->scanTmp.p, 0, sizeof(LoopState), ctx->stream));
+    if (fresh) {
+        static const LoopState init = [] { LoopState z; memset(&z, 0, sizeof z); for (float& f : z.enterFrac) f = -1.0f; return z; }();
+        KDPT_CUDA(cudaMemcpyAsync(ctx->scanTmp.p, &init, sizeof(LoopState), cudaMemcpyHostToDevice, ctx->stream));
+    }
     rb.st = ctx->scanTmp.as<LoopState>();
     rb.cap = n; rb.capPackets = (n + 31) / 32 + 1;
     if ((rc = ctx->keysTmp.ensure(2 * sizeof(int) * (size_t)rb.capPackets * batch))) return rc;
@@ -634,6 +801,7 @@ static int checkParams(const kdpt_params* p)
     if (!p) { setError("render: null params"); return KDPT_ERR_ARG; }
     if (p->mode < 0 || p->mode >= KDPT_MODE_COUNT) { setError("render: unknown traversal mode"); return KDPT_ERR_ARG; }
     if (p->sortByMaterial < 0 || p->sortByMaterial > 2) { setError("render: sortByMaterial must be 0, 1 or 2"); return KDPT_ERR_ARG; }
+    if (p->laneQueue < 0 || p->laneQueue > 2) { setError("render: laneQueue must be 0, 1 or 2"); return KDPT_ERR_ARG; }
     return KDPT_OK;
 }
 
@@ -648,6 +816,9 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
     int* pc = p.compaction ? rb.packetCount : nullptr;
     unsigned* pa = p.compaction ? rb.packetAlive : nullptr;
     static const GenArgs noGen{};
+    // kdpt_params.laneQueue (0 auto, 1 direct, 2 queued); KDPT_QUEUE=0/1/2 (direct/queued/auto) overrides it in development
+    static const int envQueue = getenv("KDPT_QUEUE") ? atoi(getenv("KDPT_QUEUE")) : -1;
+    A.queuePolicy = envQueue >= 0 ? envQueue : (p.laneQueue == 1 ? 0 : p.laneQueue == 2 ? 1 : 2);
 #define KDPT_LAUNCH_BOUNCE(M)                                                                                                   \
     if (gen) bounceKernel<M, true><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, *gen);   \
     else bounceKernel<M, false><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, noGen)
@@ -832,6 +1003,11 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
         KDPT_CUDA(cudaStreamSynchronize(s));
         memset(stats, 0, sizeof *stats);
         for (int b = 0; b < kMaxBounces; b++) stats->rayBounces += after[b] - before[b];
+        if (getenv("KDPT_DEBUG_STATS")) {
+            unsigned long long tr[kMaxBounces];
+            KDPT_CUDA(cudaMemcpy(tr, rb.st->travRays, sizeof tr, cudaMemcpyDeviceToHost));
+            for (int b = 0; b < kMaxBounces; b++) fprintf(stderr, "kdpt stats: bounce %d rays %llu (cumulative) entering the tree %llu (%.3f)\n", b, after[b], tr[b], after[b] ? (double)tr[b] / after[b] : 0.0);
+        }
         stats->launches = launches;
         KDPT_CUDA(cudaEventElapsedTime(&stats->totalMs, ctx->ev0, ctx->ev1));
         stats->intersectMs = 0.0f;

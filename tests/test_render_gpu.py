@@ -68,12 +68,13 @@ def _close(a, b, rtol=LIBM_RTOL, atol=1e-6):
 
 @pytest.mark.parametrize("name,kw", CASES)
 @pytest.mark.parametrize("mode", [kdpt.FULLSTACK, kdpt.SHORTSTACK, kdpt.REF_T1, kdpt.REF_T2])
-def test_bounce_stages_match_oracle(oracle, name, kw, mode):
+@pytest.mark.parametrize("lane_queue", [1, 2])
+def test_bounce_stages_match_oracle(oracle, name, kw, mode, lane_queue):
     """pathTraceOneBounceKDbare + shadeMaterial over three consecutive bounces, feeding the ORACLE's paths to both
     sides at every bounce so that one libm ulp cannot cascade. Hit decisions (t, normal, material, remainingBounces,
     colour) are bit-exact; the scattered ray goes through device libm -> LIBM_RTOL."""
     sc = _scene(name, 128, 128)
-    p = kdpt.default_params(mode=mode, **kw)
+    p = kdpt.default_params(mode=mode, laneQueue=lane_queue, **kw)     # both traversal schedules of the bounce kernel
     with kdpt.Context(sc) as ctx:
         paths = ctx.generate_rays(3, p)
         nhit = 0
@@ -202,6 +203,27 @@ def test_headless_cli_matches_the_library(tmp_path):
     r = subprocess.run([exe, os.path.join(scenes, "cornell8.txt"), os.path.join(scenes, "stanford_bunny.obj"), "--spp", "1",
                         "--res", "32x32", "--out", str(png)], capture_output=True, text=True)
     assert r.returncode == 0 and png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+@pytest.mark.parametrize("mode", [kdpt.FULLSTACK, kdpt.SHORTSTACK, kdpt.REF_T1])
+def test_lane_queue_schedules_are_bit_identical(name, kw, mode):
+    """kdpt_params.laneQueue only changes WHEN a path's traversal runs (at once, pooled in the per-warp queue, or the
+    kernel's own per-launch choice): images and ray counts must be identical bit for bit, with and without compaction
+    and with the material sort on every bounce"""
+    sc = _scene(name, 160, 128)
+    for extra in (dict(), dict(compaction=0, sortByMaterial=0), dict(sortByMaterial=2)):
+        got = []
+        for lq in (1, 2, 0):
+            p = kdpt.default_params(mode=mode, laneQueue=lq, **kw, **extra)
+            with kdpt.Context(sc) as ctx:
+                ctx.clear_image()
+                st = ctx.render(1, 20, 1, p)            # 20 iterations = two batches: the second one uses the measured fractions
+                got.append((ctx.image().tobytes(), int(st['ray_bounces'])))
+        assert got[0] == got[1] == got[2], (extra, [g[1] for g in got])
+    with pytest.raises(kdpt.KdptError):
+        with kdpt.Context(sc) as ctx:
+            ctx.render(1, 1, 1, kdpt.default_params(laneQueue=3))
 
 
 def test_checkpoint_resume_is_bit_identical():
