@@ -200,6 +200,12 @@ int kdpt_get_image(kdpt_ctx* ctx, float* rgb);
 int kdpt_set_image(kdpt_ctx* ctx, const float* rgb);
 /* device pointer of that buffer (for an NCCL all-reduce issued by the caller) */
 int kdpt_image_device(kdpt_ctx* ctx, float** d_rgb, int* numFloats);
+/* Sum the radiance buffers of n contexts of ONE process (one per GPU, same resolution) and leave the total in every
+ * one of them — the step that follows sample-sharded rendering. Done over NVLink peer memory by the
+ * library's own kernels: device i sums slice i of all buffers in context order (so every GPU ends with the same bits),
+ * then the slices are gathered. Needs peer access between the devices (KDPT_ERR_STATE otherwise). With one process
+ * per GPU use an NCCL all-reduce on kdpt_image_device / kdpt_bind_image instead. Synchronises all contexts. */
+int kdpt_allreduce_image(kdpt_ctx** ctxs, int n);
 
 #ifdef __cplusplus
 }

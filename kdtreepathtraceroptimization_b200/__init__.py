@@ -119,6 +119,7 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_get_image.argtypes = [vp, vp]
     lib.kdpt_set_image.argtypes = [vp, vp]
     lib.kdpt_image_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+    lib.kdpt_allreduce_image.argtypes = [ctypes.POINTER(vp), ci]
     if lib.kdpt_abi_version() != 1:
         raise KdptError("libkdpt.so ABI version mismatch")
     _lib = lib
@@ -355,3 +356,12 @@ class Context:
         n = ctypes.c_int()
         _check(self._lib.kdpt_image_device(self._h, ctypes.byref(p), ctypes.byref(n)), "kdpt_image_device")
         return p.value, n.value
+
+
+def allreduce_images(contexts: list[Context]):
+    """kdpt_allreduce_image: sum the radiance buffers of several contexts of THIS process (one per GPU) over NVLink
+    peer memory and leave the total in each (single-process multi-GPU; torchrun ranks use NCCL on the bound image)."""
+    if not contexts:
+        raise KdptError("allreduce_images: no contexts")
+    arr = (ctypes.c_void_p * len(contexts))(*[c._h for c in contexts])
+    _check(contexts[0]._lib.kdpt_allreduce_image(arr, len(contexts)), "kdpt_allreduce_image")

@@ -112,11 +112,14 @@ int kdpt_destroy(kdpt_ctx* ctx)
     for (auto& b : ctx->treeMem) b.release();
     DeviceBuffer* bufs[] = {&ctx->scene.geoms, &ctx->scene.materials, &ctx->scene.offsets, &ctx->scene.geomBounds, &ctx->rays, &ctx->tmin,
                             &ctx->hits, &ctx->counter, &ctx->image, &ctx->pathsA, &ctx->pathsB, &ctx->isects,
-                            &ctx->scanTmp, &ctx->keysTmp, &ctx->hist, &ctx->accum};
+                            &ctx->scanTmp, &ctx->keysTmp, &ctx->hist, &ctx->accum, &ctx->binTmp};
     for (auto* b : bufs) b->release();
     cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev2, ctx->ev3};
     for (auto e : evs) if (e) cudaEventDestroy(e);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
+    if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
+    if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
     delete ctx;
     return KDPT_OK;
 }
@@ -280,12 +283,35 @@ int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n
     size_t rb = sizeof(kdpt_ray) * (size_t)n, tb = sizeof(float) * (size_t)n, hb = sizeof(kdpt_hit) * (size_t)n;
     if ((rc = ctx->rays.ensure(rb)) || (rc = ctx->hits.ensure(hb)) || (t_min_in && (rc = ctx->tmin.ensure(tb)))) return rc;
     cudaStream_t s = ctx->stream;
-    // pageable host memory is fine for the caller; the copies below are ordered on the context's stream
-    KDPT_CUDA(cudaMemcpyAsync(ctx->rays.p, rays, rb, cudaMemcpyHostToDevice, s));
-    if (t_min_in) KDPT_CUDA(cudaMemcpyAsync(ctx->tmin.p, t_min_in, tb, cudaMemcpyHostToDevice, s));
-    if ((rc = launchTrace(ctx, ctx->rays.as<kdpt_ray>(), t_min_in ? ctx->tmin.as<float>() : nullptr, n, ctx->hits.as<kdpt_hit>(), mode, s))) return rc;
-    ctx->launches++;
-    KDPT_CUDA(cudaMemcpyAsync(hits, ctx->hits.p, hb, cudaMemcpyDeviceToHost, s));
+    kdpt_ray* dRays = ctx->rays.as<kdpt_ray>();
+    kdpt_hit* dHits = ctx->hits.as<kdpt_hit>();
+    float* dTmin = t_min_in ? ctx->tmin.as<float>() : nullptr;
+    // Big batches go through in slices on three streams, so that the upload of slice k+1 and the download of slice k-1
+    // overlap the traversal of slice k (full overlap needs page-locked host buffers; pageable ones still work, the
+    // copies then simply serialise). A slice is still large enough for the leaf binning to find coherent packets.
+    const int slice = n > 2 * kTraceSlice ? kTraceSlice : n;
+    if (slice < n && !ctx->copyIn) {
+        KDPT_CUDA(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
+        KDPT_CUDA(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
+        KDPT_CUDA(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
+    }
+    if (slice < n) {        // work already queued on the context's stream comes first
+        KDPT_CUDA(cudaEventRecord(ctx->evCopy, s));
+        KDPT_CUDA(cudaStreamWaitEvent(ctx->copyIn, ctx->evCopy, 0));
+        KDPT_CUDA(cudaStreamWaitEvent(ctx->copyOut, ctx->evCopy, 0));
+    }
+    for (int first = 0; first < n; first += slice) {
+        const int m = n - first < slice ? n - first : slice;
+        cudaStream_t in = slice < n ? ctx->copyIn : s, out = slice < n ? ctx->copyOut : s;
+        KDPT_CUDA(cudaMemcpyAsync(dRays + first, rays + first, sizeof(kdpt_ray) * (size_t)m, cudaMemcpyHostToDevice, in));
+        if (t_min_in) KDPT_CUDA(cudaMemcpyAsync(dTmin + first, t_min_in + first, sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, in));
+        if (in != s) { KDPT_CUDA(cudaEventRecord(ctx->evCopy, in)); KDPT_CUDA(cudaStreamWaitEvent(s, ctx->evCopy, 0)); }
+        if ((rc = launchTrace(ctx, dRays + first, dTmin ? dTmin + first : nullptr, m, dHits + first, mode, s))) return rc;
+        ctx->launches++;
+        if (out != s) { KDPT_CUDA(cudaEventRecord(ctx->evCopy, s)); KDPT_CUDA(cudaStreamWaitEvent(out, ctx->evCopy, 0)); }
+        KDPT_CUDA(cudaMemcpyAsync(hits + first, dHits + first, sizeof(kdpt_hit) * (size_t)m, cudaMemcpyDeviceToHost, out));
+    }
+    if (slice < n) KDPT_CUDA(cudaStreamSynchronize(ctx->copyOut));
     KDPT_CUDA(cudaStreamSynchronize(s));
     return KDPT_OK;
 }

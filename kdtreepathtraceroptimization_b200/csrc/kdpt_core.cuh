@@ -30,6 +30,10 @@ static inline int __float_as_int(float f) { int i; __builtin_memcpy(&i, &f, 4); 
 static inline unsigned __float_as_uint(float f) { unsigned i; __builtin_memcpy(&i, &f, 4); return i; }
 #endif
 
+#ifndef KDPT_CHUNK_PAIR
+#define KDPT_CHUNK_PAIR 0     // 1: stream two chunks of a fat leaf per step (more loads in flight, ~10 more registers)
+#endif
+
 namespace kdpt {
 
 constexpr int kMaxDepth = 32;           // deepest tree the per-ray stacks accept (reference: split(13) -> 14)
@@ -448,6 +452,22 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                 const int c = cb + (int)lane;
                 unsigned hitMask = __ballot_sync(FULL, c < nch && chunkMayHit(T, cchunk0 + c, O, INV, zlim, cslack));
                 if (!hitMask) return;
+#if KDPT_CHUNK_PAIR
+                while (hitMask) {       // two chunks per step: six independent loads in flight
+                    const int j = __ffs(hitMask) - 1;
+                    hitMask &= hitMask - 1;
+                    const int j2 = __ffs(hitMask) - 1;          // -1: none left
+                    hitMask &= hitMask - 1;
+                    const int k = (cb + j) * 32 + (int)lane, k2 = (cb + j2) * 32 + (int)lane;
+                    const bool has = k < ccount, has2 = j2 >= 0 && k2 < ccount;
+                    TriHot tr, tr2;
+                    if (has) tr = loadTri(T, cstart + k);
+                    if (has2) tr2 = loadTri(T, cstart + k2);
+                    float u, v, z;
+                    if (has && rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, tr.canon, L.tri, L);
+                    if (has2 && rayTriHit(O, D, tr2.v0, tr2.e1, tr2.e2, u, v, z)) acceptHit(T, cstart + k2, tr2.canon, O, D, u, v, z, eps, tr2.canon, L.tri, L);
+                }
+#else
                 while (hitMask) {
                     const int j = __ffs(hitMask) - 1;
                     hitMask &= hitMask - 1;
@@ -458,6 +478,7 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
                         if (rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, tr.canon, L.tri, L);
                     }
                 }
+#endif
                 // tighten the cull distance with whatever any lane has found so far (only worth it on long leaves)
                 if (nch > 32) {
                     float lz = (L.t != bestT || L.tri != bestTri) ? L.z : FLT_MAX;

@@ -48,17 +48,20 @@ struct kdpt_ctx {
     uint64_t deviceBytes = 0;
     kdpt::SceneDev scene;
     // traversal scratch
-    kdpt::DeviceBuffer rays, tmin, hits, counter;
+    kdpt::DeviceBuffer rays, tmin, hits, counter, binTmp;
     // render loop state
     kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist, accum;
     int pixelCount = 0;
     float* boundImage = nullptr;        // caller-owned radiance buffer (kdpt_bind_image)
     cudaStream_t ownStream = nullptr;   // `stream` may point at a caller's stream (kdpt_set_stream)
+    cudaStream_t copyIn = nullptr, copyOut = nullptr;   // kdpt_trace: upload / download streams of the sliced pipeline
+    cudaEvent_t evCopy = nullptr;
     uint64_t launches = 0;              // kernels launched so far
     std::vector<cudaEvent_t> eventPool; // TESTINGMODE event pairs
 };
 
 namespace kdpt {
+constexpr int kTraceSlice = 1 << 21;     // rays per slice of kdpt_trace's upload / trace / download pipeline
 // kdpt_trace.cu
 int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n, kdpt_hit* dHits, int mode,
                 cudaStream_t stream);

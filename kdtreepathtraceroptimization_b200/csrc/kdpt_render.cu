@@ -711,6 +711,38 @@ __global__ void accumulateKernel(float* __restrict__ image, const float* __restr
     }
 }
 
+// ---- radiance all-reduce over peer memory (kdpt_allreduce_image) ------------------------------------------------
+struct PeerImages { float* img[16]; int n; };
+// device `self` owns floats [lo, hi): total over all buffers in context order, written into its own buffer
+__global__ void __launch_bounds__(256)
+peerReduceSliceKernel(PeerImages pi, int self, size_t lo, size_t hi)
+{
+    // float4 body (the slice bounds are multiples of 4 except possibly the very end of the image)
+    const size_t n4 = (hi - lo) / 4;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n4; k += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = reinterpret_cast<const float4*>(pi.img[0] + lo)[k];
+        for (int j = 1; j < pi.n; j++) {
+            const float4 v = reinterpret_cast<const float4*>(pi.img[j] + lo)[k];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(pi.img[self] + lo)[k] = acc;
+    }
+    for (size_t k = lo + 4 * n4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < hi; k += (size_t)gridDim.x * blockDim.x) {
+        float acc = pi.img[0][k];
+        for (int j = 1; j < pi.n; j++) acc += pi.img[j][k];
+        pi.img[self][k] = acc;
+    }
+}
+// device `self` pulls every other device's finished slice
+__global__ void __launch_bounds__(256)
+peerGatherKernel(PeerImages pi, int self, size_t per, size_t total)
+{
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int owner = (int)(k / per) < pi.n ? (int)(k / per) : pi.n - 1;
+        if (owner != self) pi.img[self][k] = pi.img[owner][k];
+    }
+}
+
 // AoS <-> SoA for the stage-level entry points
 __global__ void packPathsKernel(const kdpt_path_segment* __restrict__ in, int n, PathSoA P, LoopState* st, int depth)
 {
@@ -909,6 +941,59 @@ int kdpt_image_device(kdpt_ctx* ctx, float** d_rgb, int* numFloats)
     KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
     *d_rgb = ctx->boundImage ? ctx->boundImage : ctx->image.as<float>();
     if (numFloats) *numFloats = 3 * ctx->pixelCount;
+    return KDPT_OK;
+}
+
+int kdpt_allreduce_image(kdpt_ctx** ctxs, int n)
+{
+    if (!ctxs || n < 1 || n > 16) { setError("kdpt_allreduce_image: need 1..16 contexts"); return KDPT_ERR_ARG; }
+    for (int i = 0; i < n; i++) if (!ctxs[i]) { setError("kdpt_allreduce_image: null context"); return KDPT_ERR_ARG; }
+    PeerImages pi; memset(&pi, 0, sizeof pi); pi.n = n;
+    int rc;
+    for (int i = 0; i < n; i++) {
+        KDPT_CUDA(cudaSetDevice(ctxs[i]->device));
+        if ((rc = ensureImage(ctxs[i]))) return rc;
+        if (ctxs[i]->pixelCount != ctxs[0]->pixelCount) { setError("kdpt_allreduce_image: resolutions differ"); return KDPT_ERR_ARG; }
+        for (int j = 0; j < i; j++) if (ctxs[j]->device == ctxs[i]->device) { setError("kdpt_allreduce_image: two contexts on one device"); return KDPT_ERR_ARG; }
+        pi.img[i] = ctxs[i]->boundImage ? ctxs[i]->boundImage : ctxs[i]->image.as<float>();
+    }
+    if (n == 1) return KDPT_OK;
+    for (int i = 0; i < n; i++) {
+        KDPT_CUDA(cudaSetDevice(ctxs[i]->device));
+        for (int j = 0; j < n; j++) {
+            if (i == j) continue;
+            int can = 0;
+            KDPT_CUDA(cudaDeviceCanAccessPeer(&can, ctxs[i]->device, ctxs[j]->device));
+            if (!can) { setError("kdpt_allreduce_image: no peer access between the devices"); return KDPT_ERR_STATE; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return cudaFail(e, "cudaDeviceEnablePeerAccess");
+        }
+    }
+    const size_t total = 3 * (size_t)ctxs[0]->pixelCount;
+    size_t per = (total + n - 1) / n;
+    per = (per + 3) & ~(size_t)3;                  // slices start on float4 boundaries
+    // every GPU has finished rendering before anyone reads its buffer
+    for (int i = 0; i < n; i++) { KDPT_CUDA(cudaSetDevice(ctxs[i]->device)); KDPT_CUDA(cudaEventRecord(ctxs[i]->ev2, ctxs[i]->stream)); }
+    for (int i = 0; i < n; i++) {
+        KDPT_CUDA(cudaSetDevice(ctxs[i]->device));
+        for (int j = 0; j < n; j++) if (j != i) KDPT_CUDA(cudaStreamWaitEvent(ctxs[i]->stream, ctxs[j]->ev2, 0));
+        const size_t lo = per * i < total ? per * i : total, hi = per * (i + 1) < total ? per * (i + 1) : total;
+        if (hi > lo) peerReduceSliceKernel<<<ctxs[i]->numSMs * 2, 256, 0, ctxs[i]->stream>>>(pi, i, lo, hi);
+        KDPT_CUDA(cudaGetLastError());
+        KDPT_CUDA(cudaEventRecord(ctxs[i]->ev3, ctxs[i]->stream));
+        ctxs[i]->launches++;
+    }
+    // every slice is final before anyone gathers it
+    for (int i = 0; i < n; i++) {
+        KDPT_CUDA(cudaSetDevice(ctxs[i]->device));
+        for (int j = 0; j < n; j++) if (j != i) KDPT_CUDA(cudaStreamWaitEvent(ctxs[i]->stream, ctxs[j]->ev3, 0));
+        peerGatherKernel<<<ctxs[i]->numSMs * 2, 256, 0, ctxs[i]->stream>>>(pi, i, per, total);
+        KDPT_CUDA(cudaGetLastError());
+        ctxs[i]->launches++;
+    }
+    // nobody's buffer changes again (next render) before all gathers have read it
+    for (int i = 0; i < n; i++) { KDPT_CUDA(cudaSetDevice(ctxs[i]->device)); KDPT_CUDA(cudaStreamSynchronize(ctxs[i]->stream)); }
     return KDPT_OK;
 }
 

@@ -34,6 +34,10 @@ def _check_scene(sc, oracle, nrays, nsample, min_hit):
         info = ctx.tree_info()
         a = ctx.trace(rays, None, kdpt.FULLSTACK)
         assert a.tobytes() == ctx.trace(rays, None, kdpt.FULLSTACK).tobytes()            # idempotent
+        # batches of >= 65 536 rays are traced in leaf order (binRaysKernel), smaller ones as given: same bytes out
+        m = min(nrays, 1 << 18)
+        small = np.concatenate([ctx.trace(rays[k:k + 32768], None, kdpt.FULLSTACK) for k in range(0, m, 32768)])
+        assert a[:m].tobytes() == small.tobytes()
         s = ctx.trace(rays, None, kdpt.SHORTSTACK)
         assert (a['tri'] != s['tri']).mean() < 2e-3                                     # differ only by the nudge (1e-5 vs 1e-4)
         r1 = ctx.trace(rays[pick], None, kdpt.REF_T1)

@@ -174,6 +174,28 @@ def test_sample_sharding_is_a_partition():
     assert np.allclose(full, parts, rtol=1e-5, atol=1e-6)
 
 
+def test_peer_allreduce_of_sample_shards():
+    """kdpt_allreduce_image: two contexts of one process, one per GPU, render disjoint sample shards; after the
+    peer-memory all-reduce both hold the same bits, equal to the single-GPU image up to float summation order"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = _scene("cornell8_stanford_bunny.npz", 200, 150)
+    p = kdpt.default_params(mode=kdpt.FULLSTACK)
+    with kdpt.Context(sc, device=0) as one:
+        one.clear_image(); one.render(1, 8, 1, p); full = one.image()
+    with kdpt.Context(sc, device=0) as a, kdpt.Context(sc, device=1) as b:
+        a.clear_image(); b.clear_image()
+        a.render_async(1, 4, 2, p); b.render_async(2, 4, 2, p)
+        kdpt.allreduce_images([a, b])
+        ia, ib = a.image(), b.image()
+    assert ia.tobytes() == ib.tobytes()
+    assert np.allclose(ia, full, rtol=1e-5, atol=1e-6)
+    with kdpt.Context(sc, device=0) as a, kdpt.Context(sc, device=0) as b:
+        with pytest.raises(kdpt.KdptError):
+            kdpt.allreduce_images([a, b])         # two contexts on one device
+
+
 def test_headless_cli_matches_the_library(tmp_path):
     """kdpt_render (C++ driver over the C ABI: scene .txt + .obj -> first-frame camera -> spp iterations -> saveImage
     semantics: x mirrored, / samples, clamp*255 truncated) writes the same pixels as the Python mirror computes"""
