@@ -151,6 +151,12 @@ int kdpt_scene_load(const char* scene_txt, const char* obj_path, const char* mtl
 /* KDtree(triangles) -> updateBbox -> split(kd_depth) -> flatten, for a caller-supplied triangle list:
  * tri18 = x1 y1 z1 x2 y2 z2 x3 y3 z3 nx1 ny1 nz1 nx2 ny2 nz2 nx3 ny3 nz3 per triangle, mtl = shape index per triangle or NULL */
 int kdpt_scene_from_triangles(const float* tri18, const int* mtl, int n, int kd_depth, kdpt_host_scene** out);
+/* The same build on the GPU (KDnode::split is the start-up bottleneck of the 1 M / 10 M-triangle
+ * configs): level-synchronous segmented partition on `device`, node numbering on the host. Output arrays are
+ * byte-identical to kdpt_scene_from_triangles's (and so to the reference builder's). device_ms (may be NULL) receives the
+ * device time between the end of the triangle upload and the last kernel. No CPU fallback: KDPT_ERR_CUDA without a device. */
+int kdpt_scene_from_triangles_gpu(const float* tri18, const int* mtl, int n, int kd_depth, int device, float* device_ms,
+                                  kdpt_host_scene** out);
 /* borrow the arrays (valid until kdpt_scene_free) */
 int kdpt_scene_view(const kdpt_host_scene* scene, kdpt_scene* view, int* iterations);
 /* source triangle (OBJ face order) of every TriBare entry */

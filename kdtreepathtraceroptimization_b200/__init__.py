@@ -107,6 +107,7 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_camera_first_frame.restype = None
     lib.kdpt_scene_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ci, ci, ctypes.POINTER(vp)]
     lib.kdpt_scene_from_triangles.argtypes = [vp, vp, ci, ci, ctypes.POINTER(vp)]
+    lib.kdpt_scene_from_triangles_gpu.argtypes = [vp, vp, ci, ci, ci, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(vp)]
     lib.kdpt_scene_view.argtypes = [vp, ctypes.POINTER(_CScene), ctypes.POINTER(ci)]
     lib.kdpt_scene_triangle_sources.argtypes = [vp]
     lib.kdpt_scene_triangle_sources.restype = ctypes.POINTER(ctypes.c_int)
@@ -190,6 +191,18 @@ class Scene:
         _check(load_library().kdpt_scene_from_triangles(_ptr(tri18), _ptr(m) if m is not None else None, len(tri18), kd_depth,
                                                         ctypes.byref(h)), "kdpt_scene_from_triangles")
         return Scene._from_host(h)
+
+    @staticmethod
+    def from_triangles_gpu(tri18: np.ndarray, mtl: np.ndarray | None = None, kd_depth: int = 13, device: int = 0) -> "Scene":
+        """the same KD build on the GPU (kdpt_scene_from_triangles_gpu); `.build_device_ms` holds the device time"""
+        tri18 = np.ascontiguousarray(tri18, dtype=np.float32).reshape(-1, 18)
+        m = np.ascontiguousarray(mtl, dtype=np.int32) if mtl is not None else None
+        h = ctypes.c_void_p(); ms = ctypes.c_float()
+        _check(load_library().kdpt_scene_from_triangles_gpu(_ptr(tri18), _ptr(m) if m is not None else None, len(tri18), kd_depth,
+                                                            device, ctypes.byref(ms), ctypes.byref(h)), "kdpt_scene_from_triangles_gpu")
+        sc = Scene._from_host(h)
+        sc.build_device_ms = float(ms.value)
+        return sc
 
     def first_frame_camera(self) -> "Scene":
         """apply the reference's main.cpp camera set-up (kdpt_camera_first_frame) and return self"""

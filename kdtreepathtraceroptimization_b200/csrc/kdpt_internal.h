@@ -65,4 +65,9 @@ constexpr int kTraceSlice = 1 << 21;     // rays per slice of kdpt_trace's uploa
 // kdpt_trace.cu
 int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n, kdpt_hit* dHits, int mode,
                 cudaStream_t stream);
+// kdpt_build.cu — KD build on the GPU; same arrays as kdpt_scene.cpp:buildTree. deviceMs (may be NULL): device time from
+// the end of the triangle upload to the last kernel, including the per-level host decisions
+int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int device,
+                    std::vector<kdpt_node_bare>& nodes, std::vector<kdpt_tri_bare>& tris, std::vector<int>& triSource,
+                    float* deviceMs);
 } // namespace kdpt

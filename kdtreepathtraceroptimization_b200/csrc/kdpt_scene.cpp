@@ -24,6 +24,9 @@
 
 namespace kdpt {
 void setError(const std::string& msg);
+// kdpt_build.cu: the same build, level-synchronous on the GPU
+int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int device, std::vector<kdpt_node_bare>& nodes,
+                    std::vector<kdpt_tri_bare>& tris, std::vector<int>& triSource, float* deviceMs);
 }
 
 namespace {
@@ -679,6 +682,21 @@ int kdpt_scene_from_triangles(const float* tri18, const int* mtl, int n, int kd_
     kdpt_material m; memset(&m, 0, sizeof m); m.color[0] = m.color[1] = m.color[2] = 1.0f;
     h->s.materials.push_back(m); h->s.offsets.push_back(0); h->s.traceDepth = 8;
     buildTree(tri18, mtl, n, kd_depth > 0 ? kd_depth : 13, h->s);
+    *out = h;
+    return KDPT_OK;
+}
+
+int kdpt_scene_from_triangles_gpu(const float* tri18, const int* mtl, int n, int kd_depth, int device, float* device_ms,
+                                  kdpt_host_scene** out)
+{
+    if (!out || n < 0 || (n > 0 && !tri18)) { kdpt::setError("kdpt_scene_from_triangles_gpu: bad argument"); return KDPT_ERR_ARG; }
+    *out = nullptr;
+    kdpt_host_scene* h = new kdpt_host_scene();
+    memset(&h->s.camera, 0, sizeof h->s.camera);
+    kdpt_material m; memset(&m, 0, sizeof m); m.color[0] = m.color[1] = m.color[2] = 1.0f;
+    h->s.materials.push_back(m); h->s.offsets.push_back(0); h->s.traceDepth = 8;
+    int rc = kdpt::buildTreeDevice(tri18, mtl, n, kd_depth > 0 ? kd_depth : 13, device, h->s.nodes, h->s.tris, h->s.triSource, device_ms);
+    if (rc != KDPT_OK) { delete h; return rc; }
     *out = h;
     return KDPT_OK;
 }

@@ -123,6 +123,14 @@ def test_no_gpu_means_loud_failure(golden_all):
         kdpt.Context(kdpt.Scene.from_npz(os.path.join(ROOT, "tests/golden/cornell_sphere_low_1.npz")))
 
 
+def test_gpu_kd_build_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(kdpt.KdptError, match="no CUDA device"):
+        kdpt.Scene.from_triangles_gpu(np.zeros((4, 18), 'f4'))
+
+
 def test_product_never_touches_the_oracle():
     """no file of the product (package, csrc, include) includes, links, loads or imports anything under oracle/
     (comments may cite it)"""
