@@ -406,7 +406,12 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
                     if (tn > tf || tf < 0.0f) continue;
                     if (w.tMin < FLT_MAX && tn * dlen > w.tMin * 1.0001f + 1e-3f) continue;
                     V3 pt, nr;
+#if KDPT_OUTLINE >= 2       // one copy of the test behind a generic pointer instead of a shared- and a global-memory copy
+                    const kdpt_geom* gp = g < ng ? &sGeoms[g] : &S.geoms[g];
+                    float tg = geomTest(*gp, w.r.o, w.r.d, pt, nr);
+#else
                     float tg = g < ng ? geomTest(sGeoms[g], w.r.o, w.r.d, pt, nr) : geomTest(S.geoms[g], w.r.o, w.r.d, pt, nr);
+#endif
                     if (tg > 0.0f && w.tMin > tg) { w.tMin = tg; w.hitGeom = g; w.ipoint = pt; w.normal = nr; }
                 }
                 // does the ray reach the tree at all? (the traversals' own first step: a miss of the root box ends them)
@@ -968,6 +973,14 @@ int kdpt_allreduce_image(kdpt_ctx** ctxs, int n)
             cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
             if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
             else if (e != cudaSuccess) return cudaFail(e, "cudaDeviceEnablePeerAccess");
+            // the contexts' own radiance buffers come from the stream-ordered pool (DeviceBuffer), whose memory is
+            // visible to a peer only after the pool says so (cudaDeviceEnablePeerAccess covers cudaMalloc memory)
+            cudaMemPool_t pool;
+            KDPT_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctxs[j]->device));
+            cudaMemAccessDesc desc; memset(&desc, 0, sizeof desc);
+            desc.location.type = cudaMemLocationTypeDevice; desc.location.id = ctxs[i]->device;
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            KDPT_CUDA(cudaMemPoolSetAccess(pool, &desc, 1));
         }
     }
     const size_t total = 3 * (size_t)ctxs[0]->pixelCount;

@@ -105,9 +105,26 @@ KDPT_HD float geomTest(const kdpt_geom& g, V3 ro, V3 rd, V3& point, V3& normal)
 }
 
 #if defined(__CUDACC__)
+// The scatter helpers below are called from up to seven places of scatterRay. Inlined everywhere (KDPT_OUTLINE 0) they
+// are ~40 % of the bounce kernel's 150-300 KB of SASS but ~3 % of its executed instructions, and that cold code is
+// interleaved with the hot loops: ncu shows "no instruction" (instruction-cache miss) as the top or second stall reason
+// of the bounce kernel. KDPT_OUTLINE 1 keeps ONE out-of-line copy of each (values in and out in registers, so the
+// arithmetic — and every result bit — is the same).
+#ifndef KDPT_OUTLINE
+#define KDPT_OUTLINE 1
+#endif
+#if KDPT_OUTLINE >= 1
+#define KDPT_SCATTER_FN __device__ __noinline__
+#else
+#define KDPT_SCATTER_FN __device__ __forceinline__
+#endif
+struct DirRng { float x, y, z; unsigned rng; };
+
 // calculateRandomDirectionInHemisphere, src/interactions.h:9-41
-__device__ __forceinline__ V3 randomHemisphere(V3 normal, Rng& rng)
+KDPT_SCATTER_FN DirRng randomHemisphereImpl(float nx, float ny, float nz, unsigned rngState)
 {
+    Rng rng; rng.x = rngState;
+    const V3 normal = mk(nx, ny, nz);
     float up = sqrtf(rng.u01());
     float over = sqrtf(1 - up * up);
     float around = rng.u01() * KDPT_TWO_PI;
@@ -117,7 +134,15 @@ __device__ __forceinline__ V3 randomHemisphere(V3 normal, Rng& rng)
     else dnn = mk(0, 0, 1);
     V3 p1 = normalize(cross(normal, dnn));
     V3 p2 = normalize(cross(normal, p1));
-    return (up * normal + (cosf(around) * over) * p1) + (sinf(around) * over) * p2;
+    const V3 d = (up * normal + (cosf(around) * over) * p1) + (sinf(around) * over) * p2;
+    DirRng o; o.x = d.x; o.y = d.y; o.z = d.z; o.rng = rng.x;
+    return o;
+}
+__device__ __forceinline__ V3 randomHemisphere(V3 normal, Rng& rng)
+{
+    const DirRng o = randomHemisphereImpl(normal.x, normal.y, normal.z, rng.x);
+    rng.x = o.rng;
+    return mk(o.x, o.y, o.z);
 }
 // rotateVector, src/interactions.h:44-65
 __device__ __forceinline__ V3 rotateVector(V3 n1, V3 axis, float angle)
@@ -137,11 +162,13 @@ __device__ __forceinline__ V3 randSpherical(float angle, Rng& rng)
     return normalize(mk((float)(cos(theta) * sin(phi)), (float)(sin(theta) * sin(phi)), (float)cos(phi)));
 }
 // getFresnelVal (Schlick), src/interactions.h:127-133
-__device__ __forceinline__ float fresnel(V3 I, V3 N, float ior)
+KDPT_SCATTER_FN float fresnelImpl(float ix, float iy, float iz, float nx, float ny, float nz, float ior)
 {
+    const V3 I = mk(ix, iy, iz), N = mk(nx, ny, nz);
     float R0 = powf((1.0f - ior) / (1.0f + ior), 2.0f);
     return (float)(R0 + (1.0f - R0) * pow((double)(1.0f - dot(N, -I)), 5.0));
 }
+__device__ __forceinline__ float fresnel(V3 I, V3 N, float ior) { return fresnelImpl(I.x, I.y, I.z, N.x, N.y, N.z, ior); }
 __device__ __forceinline__ V3 reflectG(V3 I, V3 N) { return I - (N * dot(N, I)) * 2.0f; }
 __device__ __forceinline__ V3 refractG(V3 I, V3 N, float eta)
 {
@@ -149,12 +176,22 @@ __device__ __forceinline__ V3 refractG(V3 I, V3 N, float eta)
     float k = 1.0f - eta * eta * (1.0f - dv * dv);
     return (eta * I - (eta * dv + sqrtf(k)) * N) * (float)(k >= 0.0f);
 }
-__device__ __forceinline__ V3 softJitter(V3 dir, Rng& rng, float a)
+KDPT_SCATTER_FN DirRng softJitterImpl(float dx, float dy, float dz, unsigned rngState, float a)
 {
+    Rng rng; rng.x = rngState;
+    const V3 dir = mk(dx, dy, dz);
     V3 v = randSpherical(a, rng);
     float angle = acosf(dot(mk(0.0f, 0.0f, -1.0f), dir));
     V3 axis = normalize(cross(mk(0.0f, 0.0f, -1.0f), dir));
-    return rotateVector(v, axis, angle);
+    const V3 d = rotateVector(v, axis, angle);
+    DirRng o; o.x = d.x; o.y = d.y; o.z = d.z; o.rng = rng.x;
+    return o;
+}
+__device__ __forceinline__ V3 softJitter(V3 dir, Rng& rng, float a)
+{
+    const DirRng o = softJitterImpl(dir.x, dir.y, dir.z, rng.x, a);
+    rng.x = o.rng;
+    return mk(o.x, o.y, o.z);
 }
 
 struct PathRay { V3 o, d; bool inside; float sdepth; };
