@@ -72,6 +72,19 @@ def peak_hbm():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def l2_reference(achieved):
+    """L2-resident read bandwidth measured on this pool's B200 with tools/l2_peak.cu (profiles/r1_l2_peak.json): the
+    physical ceiling of the workloads whose tree fits the 126 MB L2; informational, next to the contract's
+    HBM denominator"""
+    try:
+        z = json.load(open(os.path.join(ROOT, "profiles", "r1_l2_peak.json")))["read_gbs"]
+        pk = max(v for k, v in z.items() if int(k.split()[0]) <= 64)
+        return {"l2_read_peak_gbs": pk, "frac_of_l2": (achieved / pk) if achieved else None, "hbm_read_peak_gbs": z.get("4096 MB"),
+                "l2_source": "profiles/r1_l2_peak.json (ld.global.cg read kernel, best of 8-64 MB buffers)"}
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (recipe's clocks line)."""
 
@@ -297,7 +310,11 @@ def run_trace_workload(args):
                           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                        "traffic": measured_traffic(args.workload)[0],
                                        "kernel": "traceKernel<fullstack>", "avg_launch_ms": ms / K, "algorithmic_bytes_per_ray": bpr,
-                                       "V_nodes_per_ray": V, "T_tris_per_ray": T, "peak_source": peak_src},
+                                       "V_nodes_per_ray": V, "T_tris_per_ray": T, "peak_source": peak_src,
+                                       "traffic_gbs_at_this_speed": (measured_traffic(args.workload)[0] or 0) / (ms / K * 1e-3) / 1e9,
+                                       "note": "achieved counts the ALGORITHMIC bytes of the unculled near-first traversal (SURVEY 8d); chunk-box culling "
+                                               "and leaf-ordered ray binning make the kernel touch far fewer (traffic = ncu DRAM bytes per launch), so "
+                                               "frac > 1 and the kernel is latency/issue-bound, not HBM-bound (profiles/r1_trace_soup10m.txt)"},
                           "cpu_baseline": {"value": 20000 / dt1 / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                            "sample": "20 000 of the same rays through the reference's traverseKDbare semantics (oracle restatement)"}}), flush=True)
     ctx.close()
@@ -478,7 +495,7 @@ def main():
                     "kernel": "bounceKernel<%s>" % mode_name, "avg_launch_ms": launch_ms,
                     "kernel_share_of_step": st["intersect_ms"] / st["total_ms"],
                     "algorithmic_bytes_per_ray_bounce": ab["bytes_per_ray_bounce"], "V_nodes_per_ray": ab["V"], "T_tris_per_ray": ab["T"],
-                    "peak_source": peak_src,
+                    "peak_source": peak_src, **l2_reference(achieved),
                     "note": "tree + triangles of this workload are %d KB, i.e. L1/L2-resident: the HBM figure is the "
                             "contract's denominator, not the physical bound (see DESIGN.md)" % (ctx.tree_info()["device_bytes"] // 1024)}
         except Exception as e:      # never let the roofline bookkeeping kill the bench line
