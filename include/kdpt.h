@@ -157,6 +157,15 @@ int kdpt_scene_from_triangles(const float* tri18, const int* mtl, int n, int kd_
  * device time between the end of the triangle upload and the last kernel. No CPU fallback: KDPT_ERR_CUDA without a device. */
 int kdpt_scene_from_triangles_gpu(const float* tri18, const int* mtl, int n, int kd_depth, int device, float* device_ms,
                                   kdpt_host_scene** out);
+/* Binary scene cache: every array of a host scene in one checksummed file (same machine ABI), so
+ * that a 1 M / 10 M-triangle config starts without re-parsing the OBJ and re-building the tree. A truncated, corrupt or
+ * foreign file is refused with KDPT_ERR_ARG, never half-loaded. */
+int kdpt_scene_save(const kdpt_host_scene* scene, const char* path);
+int kdpt_scene_load_cache(const char* path, kdpt_host_scene** out);
+/* kdpt_scene_load through a content-addressed cache: the file name under cache_dir is a hash of the bytes of the scene
+ * file, the OBJ, the material libraries it names, and the build options; *cache_hit (may be NULL) says which way it went. */
+int kdpt_scene_load_cached(const char* scene_txt, const char* obj_path, const char* mtl_dir, int kd_depth, int synth_normals,
+                           const char* cache_dir, kdpt_host_scene** out, int* cache_hit);
 /* borrow the arrays (valid until kdpt_scene_free) */
 int kdpt_scene_view(const kdpt_host_scene* scene, kdpt_scene* view, int* iterations);
 /* source triangle (OBJ face order) of every TriBare entry */

@@ -108,6 +108,10 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_scene_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ci, ci, ctypes.POINTER(vp)]
     lib.kdpt_scene_from_triangles.argtypes = [vp, vp, ci, ci, ctypes.POINTER(vp)]
     lib.kdpt_scene_from_triangles_gpu.argtypes = [vp, vp, ci, ci, ci, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(vp)]
+    lib.kdpt_scene_save.argtypes = [vp, ctypes.c_char_p]
+    lib.kdpt_scene_load_cache.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.kdpt_scene_load_cached.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ci, ci, ctypes.c_char_p, ctypes.POINTER(vp),
+                                           ctypes.POINTER(ci)]
     lib.kdpt_scene_view.argtypes = [vp, ctypes.POINTER(_CScene), ctypes.POINTER(ci)]
     lib.kdpt_scene_triangle_sources.argtypes = [vp]
     lib.kdpt_scene_triangle_sources.restype = ctypes.POINTER(ctypes.c_int)
@@ -180,6 +184,24 @@ class Scene:
         _check(load_library().kdpt_scene_load(scene_txt.encode(), obj_path.encode() if obj_path else None,
                                               mtl_dir.encode() if mtl_dir else None, kd_depth, int(synth_normals),
                                               ctypes.byref(h)), "kdpt_scene_load")
+        return Scene._from_host(h)
+
+    @staticmethod
+    def load_cached(scene_txt: str, obj_path: str | None, cache_dir: str, mtl_dir: str | None = None, kd_depth: int = 13,
+                    synth_normals: bool = False) -> "Scene":
+        """`load` through the content-addressed binary cache (kdpt_scene_load_cached); `.cache_hit` says which way it went"""
+        h = ctypes.c_void_p(); hit = ctypes.c_int()
+        _check(load_library().kdpt_scene_load_cached(scene_txt.encode(), obj_path.encode() if obj_path else None,
+                                                     mtl_dir.encode() if mtl_dir else None, kd_depth, int(synth_normals),
+                                                     cache_dir.encode(), ctypes.byref(h), ctypes.byref(hit)), "kdpt_scene_load_cached")
+        sc = Scene._from_host(h)
+        sc.cache_hit = bool(hit.value)
+        return sc
+
+    @staticmethod
+    def from_cache(path: str) -> "Scene":
+        h = ctypes.c_void_p()
+        _check(load_library().kdpt_scene_load_cache(path.encode(), ctypes.byref(h)), "kdpt_scene_load_cache")
         return Scene._from_host(h)
 
     @staticmethod

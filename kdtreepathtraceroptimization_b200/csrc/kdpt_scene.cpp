@@ -701,6 +701,140 @@ int kdpt_scene_from_triangles_gpu(const float* tri18, const int* mtl, int n, int
     return KDPT_OK;
 }
 
+// ---- binary scene cache: the arrays above in one file, so that a 1 M / 10 M-triangle config starts
+// without re-parsing the OBJ and re-building the tree. Layout: magic, version, 8 counts, camera, traceDepth, iterations,
+// image name, the arrays back to back, then FNV-1a-64 of everything before it. Same-endianness, same-ABI file (the
+// PODs are the reference's own layouts); a file that does not check out is refused, never half-loaded.
+extern "C++" {
+namespace {
+const char kCacheMagic[8] = {'K', 'D', 'P', 'T', 'S', 'C', 'N', '1'};
+uint64_t fnv1a(uint64_t h, const void* p, size_t n)
+{
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+struct CacheWriter {
+    FILE* f; uint64_t h = 1469598103934665603ull; bool ok = true;
+    void put(const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) ok = false; h = fnv1a(h, p, n); }
+    template <class T> void vec(const std::vector<T>& v) { put(v.data(), v.size() * sizeof(T)); }
+};
+struct CacheReader {
+    FILE* f; uint64_t h = 1469598103934665603ull; bool ok = true;
+    void get(void* p, size_t n) { if (n && fread(p, 1, n, f) != n) ok = false; else h = fnv1a(h, p, n); }
+    template <class T> void vec(std::vector<T>& v, uint64_t count, uint64_t limit)
+    {
+        if (!ok || count > limit) { ok = false; return; }
+        v.resize((size_t)count); get(v.data(), v.size() * sizeof(T));
+    }
+};
+bool readWholeFile(const std::string& path, std::string& out)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char buf[1 << 16]; size_t n;
+    out.clear();
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    fclose(f);
+    return true;
+}
+} // namespace
+} // extern "C++"
+
+int kdpt_scene_save(const kdpt_host_scene* hsc, const char* path)
+{
+    if (!hsc || !path) { kdpt::setError("kdpt_scene_save: null argument"); return KDPT_ERR_ARG; }
+    const HostScene& s = hsc->s;
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { kdpt::setError(std::string("kdpt_scene_save: cannot write ") + tmp); return KDPT_ERR_ARG; }
+    CacheWriter w{f};
+    w.put(kCacheMagic, 8);
+    const uint64_t hdr[10] = {1, s.nodes.size(), s.tris.size(), s.triSource.size(), s.geoms.size(), s.materials.size(), s.offsets.size(),
+                              (uint64_t)(int64_t)s.traceDepth, (uint64_t)(int64_t)s.iterations, s.imageName.size()};
+    w.put(hdr, sizeof hdr);
+    w.put(&s.camera, sizeof s.camera);
+    w.put(s.imageName.data(), s.imageName.size());
+    w.vec(s.nodes); w.vec(s.tris); w.vec(s.triSource); w.vec(s.geoms); w.vec(s.materials); w.vec(s.offsets);
+    const uint64_t sum = w.h;
+    if (fwrite(&sum, 1, 8, f) != 8) w.ok = false;
+    if (fclose(f) != 0) w.ok = false;
+    if (!w.ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); kdpt::setError(std::string("kdpt_scene_save: write failed: ") + path); return KDPT_ERR_ARG; }
+    return KDPT_OK;
+}
+
+int kdpt_scene_load_cache(const char* path, kdpt_host_scene** out)
+{
+    if (!path || !out) { kdpt::setError("kdpt_scene_load_cache: null argument"); return KDPT_ERR_ARG; }
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) { kdpt::setError(std::string("kdpt_scene_load_cache: cannot open ") + path); return KDPT_ERR_ARG; }
+    fseek(f, 0, SEEK_END);
+    const uint64_t fileBytes = (uint64_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    kdpt_host_scene* h = new kdpt_host_scene();
+    HostScene& s = h->s;
+    CacheReader r{f};
+    char magic[8]; uint64_t hdr[10] = {0};
+    r.get(magic, 8); r.get(hdr, sizeof hdr);
+    if (r.ok && (memcmp(magic, kCacheMagic, 8) != 0 || hdr[0] != 1)) r.ok = false;
+    if (r.ok) {
+        r.get(&s.camera, sizeof s.camera);
+        s.traceDepth = (int)(int64_t)hdr[7]; s.iterations = (int)(int64_t)hdr[8];
+        if (hdr[9] > 4096) r.ok = false;
+        else { s.imageName.resize((size_t)hdr[9]); r.get(&s.imageName[0], s.imageName.size()); }
+        // counts are bounded by the file size before anything is allocated
+        r.vec(s.nodes, hdr[1], fileBytes / sizeof(kdpt_node_bare)); r.vec(s.tris, hdr[2], fileBytes / sizeof(kdpt_tri_bare));
+        r.vec(s.triSource, hdr[3], fileBytes / sizeof(int)); r.vec(s.geoms, hdr[4], fileBytes / sizeof(kdpt_geom));
+        r.vec(s.materials, hdr[5], fileBytes / sizeof(kdpt_material)); r.vec(s.offsets, hdr[6], fileBytes / sizeof(int));
+    }
+    uint64_t sum = 0;
+    const uint64_t expect = r.h;
+    if (r.ok && (fread(&sum, 1, 8, f) != 8 || sum != expect || fgetc(f) != EOF)) r.ok = false;
+    fclose(f);
+    if (!r.ok) { delete h; kdpt::setError(std::string("kdpt_scene_load_cache: not a valid scene cache (truncated, corrupt or another version): ") + path); return KDPT_ERR_ARG; }
+    *out = h;
+    return KDPT_OK;
+}
+
+int kdpt_scene_load_cached(const char* scene_txt, const char* obj_path, const char* mtl_dir, int kd_depth, int synth_normals,
+                           const char* cache_dir, kdpt_host_scene** out, int* cache_hit)
+{
+    if (!scene_txt || !out || !cache_dir) { kdpt::setError("kdpt_scene_load_cached: null argument"); return KDPT_ERR_ARG; }
+    if (cache_hit) *cache_hit = 0;
+    // content address: the bytes of the scene file, the OBJ and every material library it names, plus the build options
+    uint64_t key = 1469598103934665603ull;
+    std::string bytes;
+    if (!readWholeFile(scene_txt, bytes)) { kdpt::setError(std::string("kdpt_scene_load_cached: cannot read ") + scene_txt); return KDPT_ERR_ARG; }
+    key = fnv1a(key, bytes.data(), bytes.size());
+    std::string dir = mtl_dir ? mtl_dir : "";
+    if (obj_path && obj_path[0]) {
+        if (!mtl_dir) { std::string p = obj_path; size_t k = p.find_last_of("/\\"); dir = k == std::string::npos ? "" : p.substr(0, k + 1); }
+        if (!readWholeFile(obj_path, bytes)) { kdpt::setError(std::string("kdpt_scene_load_cached: cannot read ") + obj_path); return KDPT_ERR_ARG; }
+        key = fnv1a(key, "\0obj", 4); key = fnv1a(key, bytes.data(), bytes.size());
+        std::istringstream in(bytes);
+        std::string line, lib;
+        while (safeGetline(in, line)) {
+            if (line.compare(0, 7, "mtllib ") == 0 || line.compare(0, 7, "mtllib\t") == 0) {
+                std::vector<std::string> t = tokenize(line);
+                if (t.size() > 1 && readWholeFile(dir + t[1], lib)) { key = fnv1a(key, "\0mtl", 4); key = fnv1a(key, lib.data(), lib.size()); }
+            }
+        }
+    }
+    const int opts[3] = {kd_depth > 0 ? kd_depth : 13, synth_normals ? 1 : 0, (int)sizeof(kdpt_geom)};
+    key = fnv1a(key, opts, sizeof opts);
+    char name[64];
+    snprintf(name, sizeof name, "kdpt-%016llx.scn", (unsigned long long)key);
+    std::string path = std::string(cache_dir);
+    if (!path.empty() && path.back() != '/') path += '/';
+    path += name;
+    if (kdpt_scene_load_cache(path.c_str(), out) == KDPT_OK) { if (cache_hit) *cache_hit = 1; return KDPT_OK; }
+    int rc = kdpt_scene_load(scene_txt, obj_path, mtl_dir, kd_depth, synth_normals, out);
+    if (rc != KDPT_OK) return rc;
+    kdpt_scene_save(*out, path.c_str());          // best effort: an unwritable cache directory does not fail the load
+    return KDPT_OK;
+}
+
 int kdpt_scene_view(const kdpt_host_scene* h, kdpt_scene* view, int* iterations)
 {
     if (!h || !view) { kdpt::setError("kdpt_scene_view: null argument"); return KDPT_ERR_ARG; }

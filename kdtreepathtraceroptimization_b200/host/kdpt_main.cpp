@@ -21,7 +21,10 @@ static void usage()
             "  --mode M           ref_t2 (default, = SHORTSTACK on), ref_t1, shortstack, fullstack\n"
             "  --no-aa  --dof-angle A  --focal F  --softness S  --sss  --no-compaction  --sort 0|1|2\n"
             "  --kd-depth D       KD build depth (default 13)   --synth-normals   --device N\n"
-            "  --out FILE         .png (8-bit, like the reference), .pfm (float radiance / spp) or .ppm\n"
+            "  --out FILE         .png (8-bit, like the reference's savePNG), .hdr (Radiance RGBE, its saveHDR), .pfm or .ppm\n"
+            "  --cache-dir DIR    content-addressed binary cache of the loaded scene + KD tree (skips OBJ parse and build)\n"
+            "  --checkpoint FILE  write the accumulation buffer + sample count there (at the end and every --checkpoint-every N)\n"
+            "  --resume FILE      continue a render from such a file (same scene and resolution)\n"
             "  --json             print one JSON line with timings\n");
 }
 
@@ -68,12 +71,58 @@ static bool writePng(const char* path, const uint8_t* rgb, int w, int h)
     return true;
 }
 
+// Radiance .hdr (what stbi_write_hdr produces for image::saveHDR, image.cpp:40-44), flat RGBE scanlines
+static bool writeHdr(const char* path, const float* rgb, int w, int h)
+{
+    FILE* f = fopen(path, "wb");
+    if (!f) return false;
+    fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", h, w);
+    std::vector<uint8_t> row((size_t)w * 4);
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            const float* px = rgb + 3 * ((size_t)y * w + x);
+            float m = px[0] > px[1] ? (px[0] > px[2] ? px[0] : px[2]) : (px[1] > px[2] ? px[1] : px[2]);
+            uint8_t* o = &row[(size_t)x * 4];
+            if (!(m >= 1e-32f)) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
+            int e; float n = frexpf(m, &e) * 256.0f / m;
+            o[0] = (uint8_t)(px[0] * n); o[1] = (uint8_t)(px[1] * n); o[2] = (uint8_t)(px[2] * n); o[3] = (uint8_t)(e + 128);
+        }
+        fwrite(row.data(), 1, row.size(), f);
+    }
+    fclose(f);
+    return true;
+}
+
+// checkpoint of a long render: "KDPTCKP1", W, H, samples rendered so far, W*H*3 floats (the accumulation buffer)
+static bool writeCheckpoint(const std::string& path, const std::vector<float>& img, int w, int h, int samples)
+{
+    const std::string tmp = path + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    const int hdr[3] = {w, h, samples};
+    bool ok = fwrite("KDPTCKP1", 1, 8, f) == 8 && fwrite(hdr, sizeof(int), 3, f) == 3 && fwrite(img.data(), sizeof(float), img.size(), f) == img.size();
+    ok = fclose(f) == 0 && ok;
+    return ok && rename(tmp.c_str(), path.c_str()) == 0;
+}
+static bool readCheckpoint(const std::string& path, std::vector<float>& img, int w, int h, int* samples)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char magic[8]; int hdr[3];
+    bool ok = fread(magic, 1, 8, f) == 8 && !memcmp(magic, "KDPTCKP1", 8) && fread(hdr, sizeof(int), 3, f) == 3 && hdr[0] == w && hdr[1] == h && hdr[2] >= 0;
+    if (ok) { img.resize((size_t)w * h * 3); ok = fread(img.data(), sizeof(float), img.size(), f) == img.size(); }
+    fclose(f);
+    if (ok) *samples = hdr[2];
+    return ok;
+}
+
 static int fail(const char* what) { fprintf(stderr, "kdpt_render: %s: %s\n", what, kdpt_last_error()); return 1; }
 
 int main(int argc, char** argv)
 {
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) { usage(); return argc < 2 ? 2 : 0; }
-    std::string sceneTxt = argv[1], obj, out = "";
+    std::string sceneTxt = argv[1], obj, out = "", cacheDir, ckpt, resume;
+    int ckptEvery = 0, cacheHit = 0, done = 0;
     int spp = -1, resW = 0, resH = 0, kdDepth = 13, synth = 0, device = 0, json = 0;
     kdpt_params p; memset(&p, 0, sizeof p);
     p.focalLength = 6.0f; p.dofAngle = 0.0f; p.softness = 0.0f; p.antialias = 1; p.enableSss = 0; p.compaction = 1;
@@ -100,12 +149,18 @@ int main(int argc, char** argv)
         else if (a == "--synth-normals") synth = 1;
         else if (a == "--device") device = atoi(next());
         else if (a == "--out") out = next();
+        else if (a == "--cache-dir") cacheDir = next();
+        else if (a == "--checkpoint") ckpt = next();
+        else if (a == "--checkpoint-every") ckptEvery = atoi(next());
+        else if (a == "--resume") resume = next();
         else if (a == "--json") json = 1;
         else if (a.size() && a[0] != '-' && obj.empty()) obj = a;
         else { usage(); return 2; }
     }
     kdpt_host_scene* hs = nullptr;
-    if (kdpt_scene_load(sceneTxt.c_str(), obj.empty() ? nullptr : obj.c_str(), nullptr, kdDepth, synth, &hs)) return fail("scene");
+    if (!cacheDir.empty()) {
+        if (kdpt_scene_load_cached(sceneTxt.c_str(), obj.empty() ? nullptr : obj.c_str(), nullptr, kdDepth, synth, cacheDir.c_str(), &hs, &cacheHit)) return fail("scene");
+    } else if (kdpt_scene_load(sceneTxt.c_str(), obj.empty() ? nullptr : obj.c_str(), nullptr, kdDepth, synth, &hs)) return fail("scene");
     kdpt_scene sc; int iterations = 0;
     kdpt_scene_view(hs, &sc, &iterations);
     if (resW > 0 && resH > 0) {                                       // scene.cpp:216-223 with the new RES
@@ -121,14 +176,37 @@ int main(int argc, char** argv)
     kdpt_ctx* ctx = nullptr;
     if (kdpt_create(&sc, device, &ctx)) return fail("create");
     kdpt_render_stats st; memset(&st, 0, sizeof st);
-    if (kdpt_render(ctx, 1, spp, 1, &p, &st)) return fail("render");
     std::vector<float> img((size_t)W * H * 3);
+    if (!resume.empty()) {       // the reference cannot do this: its buffer is lost with the process
+        if (!readCheckpoint(resume, img, W, H, &done)) { fprintf(stderr, "kdpt_render: %s is not a checkpoint of a %dx%d render\n", resume.c_str(), W, H); return 1; }
+        if (kdpt_set_image(ctx, img.data())) return fail("set_image");
+    }
+    // iterations done+1 .. spp, in slices when checkpoints are wanted (iteration numbers seed the RNG, so a resumed
+    // render produces the same image as an uninterrupted one)
+    while (done < spp) {
+        const int n = (!ckpt.empty() && ckptEvery > 0 && ckptEvery < spp - done) ? ckptEvery : spp - done;
+        kdpt_render_stats part; memset(&part, 0, sizeof part);
+        if (kdpt_render(ctx, done + 1, n, 1, &p, &part)) return fail("render");
+        st.rayBounces += part.rayBounces; st.launches += part.launches; st.totalMs += part.totalMs; st.intersectMs += part.intersectMs;
+        done += n;
+        if (!ckpt.empty()) {
+            if (kdpt_get_image(ctx, img.data())) return fail("get_image");
+            if (!writeCheckpoint(ckpt, img, W, H, done)) { fprintf(stderr, "kdpt_render: cannot write %s\n", ckpt.c_str()); return 1; }
+        }
+    }
     if (kdpt_get_image(ctx, img.data())) return fail("get_image");
     if (!out.empty()) {
         const float samples = (float)(spp > 0 ? spp : 1);
         bool pfm = out.size() > 4 && out.substr(out.size() - 4) == ".pfm";
         bool ppm = out.size() > 4 && out.substr(out.size() - 4) == ".ppm";
-        if (pfm) {
+        bool hdr = out.size() > 4 && out.substr(out.size() - 4) == ".hdr";
+        if (hdr) {
+            std::vector<float> lin((size_t)W * H * 3);
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++)
+                    for (int c = 0; c < 3; c++) lin[3 * ((size_t)y * W + (W - 1 - x)) + c] = img[3 * ((size_t)y * W + x) + c] / samples;
+            if (!writeHdr(out.c_str(), lin.data(), W, H)) { fprintf(stderr, "kdpt_render: cannot write %s\n", out.c_str()); return 1; }
+        } else if (pfm) {
             FILE* f = fopen(out.c_str(), "wb");
             if (!f) { fprintf(stderr, "kdpt_render: cannot write %s\n", out.c_str()); return 1; }
             fprintf(f, "PF\n%d %d\n-1.0\n", W, H);
@@ -153,10 +231,10 @@ int main(int argc, char** argv)
     }
     if (json)
         printf("{\"scene\": \"%s\", \"mesh\": \"%s\", \"resolution\": [%d, %d], \"spp\": %d, \"ray_bounces\": %llu, \"ms\": %.3f, "
-               "\"mrays_per_s\": %.2f, \"spp_per_s\": %.2f, \"launches\": %llu}\n",
+               "\"mrays_per_s\": %.2f, \"spp_per_s\": %.2f, \"launches\": %llu, \"cache_hit\": %d}\n",
                sceneTxt.c_str(), obj.c_str(), W, H, spp, (unsigned long long)st.rayBounces, st.totalMs,
                st.totalMs > 0 ? st.rayBounces / (st.totalMs * 1e3) : 0.0, st.totalMs > 0 ? spp / (st.totalMs * 1e-3) : 0.0,
-               (unsigned long long)st.launches);
+               (unsigned long long)st.launches, cacheHit);
     kdpt_destroy(ctx);
     kdpt_scene_free(hs);
     return 0;

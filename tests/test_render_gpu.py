@@ -227,6 +227,44 @@ def test_headless_cli_matches_the_library(tmp_path):
     assert r.returncode == 0 and png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
 
 
+def test_headless_cli_checkpoint_resume_cache_and_hdr(tmp_path):
+    """kdpt_render: a render interrupted after 4 of 10 samples and resumed from its checkpoint writes the same bytes as an
+    uninterrupted one (iteration numbers seed the RNG; accumulation is in iteration order); the scene cache is hit on
+    the second run; the .hdr output decodes to radiance / spp within RGBE precision"""
+    import json, subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "kdtreepathtraceroptimization_b200", "kdpt_render")
+    scenes = os.path.join(GOLDEN, "scenes")
+    base = [exe, os.path.join(scenes, "cornell8.txt"), os.path.join(scenes, "stanford_bunny.obj"), "--res", "80x60", "--mode", "shortstack",
+            "--cache-dir", str(tmp_path), "--json"]
+
+    def run(*extra):
+        r = subprocess.run(base + list(extra), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    full = run("--spp", "10", "--out", str(tmp_path / "full.pfm"), "--checkpoint", str(tmp_path / "full.ckp"), "--checkpoint-every", "3")
+    assert full["cache_hit"] == 0
+    part = run("--spp", "4", "--checkpoint", str(tmp_path / "part.ckp"))
+    assert part["cache_hit"] == 1
+    rest = run("--spp", "10", "--resume", str(tmp_path / "part.ckp"), "--out", str(tmp_path / "resumed.pfm"), "--checkpoint", str(tmp_path / "resumed.ckp"))
+    assert (tmp_path / "full.pfm").read_bytes() == (tmp_path / "resumed.pfm").read_bytes()
+    assert (tmp_path / "full.ckp").read_bytes() == (tmp_path / "resumed.ckp").read_bytes()
+    assert part["ray_bounces"] + rest["ray_bounces"] == full["ray_bounces"]
+    r = subprocess.run(base + ["--spp", "10", "--res", "64x64", "--resume", str(tmp_path / "part.ckp")], capture_output=True, text=True)
+    assert r.returncode != 0 and "not a checkpoint" in r.stderr                    # other resolution
+    run("--spp", "10", "--resume", str(tmp_path / "full.ckp"), "--out", str(tmp_path / "img.hdr"))   # nothing left to render
+    raw = (tmp_path / "img.hdr").read_bytes()
+    head = b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 60 +X 80\n"
+    assert raw.startswith(head) and len(raw) == len(head) + 80 * 60 * 4
+    rgbe = np.frombuffer(raw[len(head):], np.uint8).reshape(60, 80, 4).astype(np.float64)
+    dec = rgbe[..., :3] * np.exp2(rgbe[..., 3:] - 136.0) * (rgbe[..., 3:] > 0)
+    pfm = (tmp_path / "full.pfm").read_bytes()
+    ph = b"PF\n80 60\n-1.0\n"
+    want = np.frombuffer(pfm[len(ph):], '<f4').reshape(60, 80, 3)[::-1]                # PFM rows are bottom-up
+    scale = np.maximum(want.max(axis=2, keepdims=True), 1e-30)
+    assert (np.abs(dec - want) <= scale / 128 + 1e-30).all() and want.max() > 0
+
+
 @pytest.mark.parametrize("name,kw", CASES)
 @pytest.mark.parametrize("mode", [kdpt.FULLSTACK, kdpt.SHORTSTACK, kdpt.REF_T1])
 def test_lane_queue_schedules_are_bit_identical(name, kw, mode):

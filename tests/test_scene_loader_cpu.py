@@ -69,3 +69,57 @@ def test_loader_errors_and_normal_synthesis(tmp_path):
         kdpt.Scene.load(txt, str(bad))
     only = kdpt.Scene.load(txt)                                     # scene without a mesh
     assert len(only.nodes) == 0 and len(only.geoms) == 6
+
+
+def _same_scene(a, b):
+    for name in ("nodes", "tris", "geoms", "materials", "offsets", "camera", "tri_source"):
+        assert getattr(a, name).tobytes() == getattr(b, name).tobytes(), name
+    assert a.trace_depth == b.trace_depth and a.iterations == b.iterations
+
+
+def test_binary_scene_cache_round_trip_and_invalidation(tmp_path):
+    """kdpt_scene_load_cached: miss -> build + save, hit -> the same bytes without parsing; the key is the content of the
+    scene file, the OBJ, its material library and the build options; damaged files are refused, not half-loaded"""
+    import shutil
+    work = tmp_path / "scene"; cache = tmp_path / "cache"
+    work.mkdir(); cache.mkdir()
+    for f in ("cornell8.txt", "stanford_bunny.obj", "stanford_bunny.mtl"):
+        shutil.copy(os.path.join(SCENES, f), work / f)
+    txt, obj = str(work / "cornell8.txt"), str(work / "stanford_bunny.obj")
+    direct = kdpt.Scene.load(txt, obj)
+    first = kdpt.Scene.load_cached(txt, obj, str(cache))
+    assert not first.cache_hit
+    files = sorted(os.listdir(cache))
+    assert len(files) == 1 and files[0].startswith("kdpt-") and files[0].endswith(".scn")
+    second = kdpt.Scene.load_cached(txt, obj, str(cache))
+    assert second.cache_hit
+    _same_scene(direct, first); _same_scene(direct, second)
+    _same_scene(direct, kdpt.Scene.from_cache(str(cache / files[0])))
+    # other build options, a touched material library or a touched scene file are other cache entries
+    assert not kdpt.Scene.load_cached(txt, obj, str(cache), kd_depth=5).cache_hit
+    with open(work / "stanford_bunny.mtl", "a") as f:
+        f.write("\n# touched\n")
+    assert not kdpt.Scene.load_cached(txt, obj, str(cache)).cache_hit
+    with open(txt, "a") as f:
+        f.write("\n")
+    assert not kdpt.Scene.load_cached(txt, obj, str(cache)).cache_hit
+    assert len(os.listdir(cache)) == 4
+    # damage: truncation, a flipped payload byte, trailing garbage, a foreign file
+    good = (cache / files[0]).read_bytes()
+    for name, data in (("trunc", good[:len(good) // 2]), ("flip", good[:200] + bytes([good[200] ^ 1]) + good[201:]),
+                       ("tail", good + b"x"), ("foreign", b"P6\n1 1\n255\n\0\0\0"), ("empty", b"")):
+        p = tmp_path / (name + ".scn")
+        p.write_bytes(data)
+        with pytest.raises(kdpt.KdptError, match="not a valid scene cache"):
+            kdpt.Scene.from_cache(str(p))
+    with pytest.raises(kdpt.KdptError, match="cannot open"):
+        kdpt.Scene.from_cache(str(tmp_path / "missing.scn"))
+    # a damaged entry in the cache directory is rebuilt, not trusted
+    (cache / files[0]).write_bytes(good[:100])
+    os.remove(txt); shutil.copy(os.path.join(SCENES, "cornell8.txt"), txt)
+    with open(work / "stanford_bunny.mtl", "w") as f:
+        f.write(open(os.path.join(SCENES, "stanford_bunny.mtl")).read())
+    again = kdpt.Scene.load_cached(txt, obj, str(cache))
+    assert not again.cache_hit
+    _same_scene(direct, again)
+    assert (cache / files[0]).read_bytes() == good
