@@ -467,8 +467,6 @@ int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int
     }
 
     // ---- leaf lists in DFS order + TriBare records -----------------------------------------------------------------
-    outSource.assign(poolSize, 0);
-    outTris.resize(poolSize);
     if (poolSize > 0) {
         if ((rc = dLeafTri.alloc(sizeof(int) * poolSize)) || (rc = dLeaves.alloc(sizeof(LeafCopy) * leaves.size())) ||
             (rc = dOut.alloc(sizeof(kdpt_tri_bare) * poolSize))) return rc;
@@ -481,11 +479,16 @@ int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int
                                                                                           dLeafTri.as<int>(), words, dOut.as<unsigned>());
         KDPT_CUDA(cudaGetLastError());
         KDPT_CUDA(cudaEventRecord(e1, st));
+        outSource.resize(poolSize);          // the host arrays are allocated (and page-faulted) while the kernels run
+        outTris.resize(poolSize);
         KDPT_CUDA(cudaMemcpyAsync(outSource.data(), dLeafTri.p, sizeof(int) * poolSize, cudaMemcpyDeviceToHost, st));
         KDPT_CUDA(cudaMemcpyAsync(outTris.data(), dOut.p, sizeof(kdpt_tri_bare) * poolSize, cudaMemcpyDeviceToHost, st));
         KDPT_CUDA(cudaStreamSynchronize(st));
         if (deviceMs) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); *deviceMs = ms; }
-    } else if (deviceMs) *deviceMs = 0.f;
+    } else {
+        outSource.clear(); outTris.clear();
+        if (deviceMs) *deviceMs = 0.f;
+    }
     return KDPT_OK;
 }
 
