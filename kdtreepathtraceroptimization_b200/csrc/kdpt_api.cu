@@ -289,7 +289,9 @@ int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n
     // Big batches go through in slices on three streams, so that the upload of slice k+1 and the download of slice k-1
     // overlap the traversal of slice k (full overlap needs page-locked host buffers; pageable ones still work, the
     // copies then simply serialise). A slice is still large enough for the leaf binning to find coherent packets.
-    const int slice = n > 2 * kTraceSlice ? kTraceSlice : n;
+    static const int envSlice = getenv("KDPT_TRACE_SLICE") ? atoi(getenv("KDPT_TRACE_SLICE")) : 0;     // development override
+    const int sliceRays = envSlice > 0 ? envSlice : kTraceSlice;
+    const int slice = n > 2 * sliceRays ? sliceRays : n;
     if (slice < n && !ctx->copyIn) {
         KDPT_CUDA(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
         KDPT_CUDA(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));

@@ -61,7 +61,7 @@ struct kdpt_ctx {
 };
 
 namespace kdpt {
-constexpr int kTraceSlice = 1 << 21;     // rays per slice of kdpt_trace's upload / trace / download pipeline
+XX
 // kdpt_trace.cu
 int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n, kdpt_hit* dHits, int mode,
                 cudaStream_t stream);
