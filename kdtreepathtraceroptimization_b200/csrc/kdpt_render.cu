@@ -43,7 +43,12 @@ struct IterConst {
     float qw, qx, qy, qz;      // DOF rotation quaternion
 };
 
-constexpr int kMaxBatch = 16;           // iterations (samples) processed together by every launch
+#ifndef KDPT_MAX_BATCH
+#define KDPT_MAX_BATCH 64
+#endif
+constexpr int kMaxBatch = KDPT_MAX_BATCH;   // iterations (samples) processed together by every launch
+constexpr int kSegShift = 26;               // the lane queue packs (segment, path index) in one word: <= 64 segments, < 2^26 paths each
+static_assert(kMaxBatch <= 64, "the lane queue packs the segment in 6 bits");
 constexpr int kTicketPackets = 1;       // 32-path packets a warp takes per ticket (amortises the atomic + segment lookup)
 
 struct LoopState {
@@ -347,7 +352,7 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
                 w.hitGeom = __float_as_int(def[15][e]);
                 w.ipoint = mk(def[16][e], def[17][e], def[18][e]); w.normal = mk(def[19][e], def[20][e], def[21][e]);
                 const int segi = __float_as_int(def[22][e]);
-                w.seg = (int)((unsigned)segi >> 27); w.i = segi & 0x7ffffff; w.packet = w.i >> 5;
+                w.seg = (int)((unsigned)segi >> kSegShift); w.i = segi & ((1 << kSegShift) - 1); w.packet = w.i >> 5;
             }
             finishNow = have; doIsect = true;
             qHead = (qHead + nq) & (kSlots - 1);
@@ -437,7 +442,7 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
                     def[15][e] = __int_as_float(w.hitGeom);
                     def[16][e] = w.ipoint.x; def[17][e] = w.ipoint.y; def[18][e] = w.ipoint.z;
                     def[19][e] = w.normal.x; def[20][e] = w.normal.y; def[21][e] = w.normal.z;
-                    def[22][e] = __int_as_float((w.seg << 27) | w.i);
+                    def[22][e] = __int_as_float((int)(((unsigned)w.seg << kSegShift) | (unsigned)w.i));
                 }
                 defCount += __popc(defMask);
                 // camera rays (first bounce) are coherent: a packet's rays that reach the mesh are traversed together at
@@ -1019,6 +1024,7 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     if ((rc = ensureImage(ctx))) return rc;
     const kdpt_params& p = *params;
     const int n = ctx->pixelCount;
+    if (n >= (1 << kSegShift)) { setError("kdpt_render: more than 2^26 pixels"); return KDPT_ERR_ARG; }
     // iterations per launch: bounded by kMaxBatch and by 8 GB of path state (of 180 GB)
     int maxBatch = kMaxBatch;
     while (maxBatch > 1 && (size_t)maxBatch * n * 128 > ((size_t)8 << 30)) maxBatch >>= 1;
@@ -1149,6 +1155,7 @@ int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, k
         return KDPT_ERR_ARG;
     }
     if (stages == KDPT_STAGE_SHADE && !isects) { setError("kdpt_bounce: the shade stage alone needs the intersections"); return KDPT_ERR_ARG; }
+    if (n >= (1 << kSegShift)) { setError("kdpt_bounce: more than 2^26 paths"); return KDPT_ERR_ARG; }
     int rc = checkParams(params);
     if (rc) return rc;
     if (n == 0) return KDPT_OK;
