@@ -74,9 +74,13 @@ struct IterConsts { IterConst c[kMaxBatch]; };
 // `per` consecutive 32-path packets of one segment
 __device__ __forceinline__ void buildPacketPrefix(int* pk, const LoopState* st, int B, int depth, int per)
 {
+    // the per-segment counts are fetched by B threads at once (one L2 round trip instead of B dependent ones: with 64
+    // segments the serial form cost every launch ~25 us before its first packet), then summed from shared memory
+    for (int s = threadIdx.x; s < B; s += blockDim.x) pk[s + 1] = (((st->np[s][depth] + 31) >> 5) + per - 1) / per;
+    __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int s = 0; s < B; s++) { pk[s] = acc; acc += (((st->np[s][depth] + 31) >> 5) + per - 1) / per; }
+        for (int s = 0; s < B; s++) { const int c = pk[s + 1]; pk[s] = acc; acc += c; }
         pk[B] = acc;
     }
     __syncthreads();
@@ -591,17 +595,21 @@ compactScatterKernel(PathSoA P, PathSoA Q, const int* __restrict__ packetOffset,
 {
     const unsigned lane = threadIdx.x & 31u;
     const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, numWarps = (gridDim.x * blockDim.x) >> 5;
-    for (int seg = 0; seg < bt.B; seg++) {
-        const int n = st->np[seg][depth];
-        const int numPackets = (n + 31) >> 5;
-        for (int packet = warpId; packet < numPackets; packet += numWarps) {      // uniform work: static striding
-            const unsigned i = (unsigned)packet * 32u + lane;
-            const size_t slot = (size_t)seg * bt.cap + i;
-            const unsigned mask = packetAlive[seg * bt.capPackets + packet];   // remainingBounces != 0 (is_zero_bounce, pathtrace.cu:103-110)
-            if ((mask >> lane) & 1u) {
-                size_t dst = (size_t)seg * bt.cap + packetOffset[seg * bt.capPackets + packet] + __popc(mask & ((1u << lane) - 1u));
-                Q.od[dst] = P.od[slot]; Q.dr[dst] = P.dr[slot]; Q.cp[dst] = P.cp[slot]; Q.bm[dst] = P.bm[slot];
-            }
+    // one flat packet space over the batched iterations (as in the bounce kernel): a loop over the segments would pay
+    // one dependent L2 round trip per segment and warp before doing anything
+    __shared__ int pk[kMaxBatch + 1];
+    buildPacketPrefix(pk, st, bt.B, depth, 1);
+    const int total = pk[bt.B];
+    int seg = 0;
+    for (int t = warpId; t < total; t += numWarps) {      // uniform work: static striding; a warp's tickets only grow
+        while (seg + 1 < bt.B && t >= pk[seg + 1]) seg++;
+        const int packet = t - pk[seg];
+        const unsigned i = (unsigned)packet * 32u + lane;
+        const size_t slot = (size_t)seg * bt.cap + i;
+        const unsigned mask = packetAlive[seg * bt.capPackets + packet];   // remainingBounces != 0 (is_zero_bounce, pathtrace.cu:103-110)
+        if ((mask >> lane) & 1u) {
+            size_t dst = (size_t)seg * bt.cap + packetOffset[seg * bt.capPackets + packet] + __popc(mask & ((1u << lane) - 1u));
+            Q.od[dst] = P.od[slot]; Q.dr[dst] = P.dr[slot]; Q.cp[dst] = P.cp[slot]; Q.bm[dst] = P.bm[slot];
         }
     }
 }
