@@ -1,0 +1,43 @@
+// pathtrace_kdpt.cpp — the drop-in for the reference's src/pathtrace.cu that INTEGRATION.md describes: the three functions
+// of src/pathtrace.h (6-21) implemented on libkdpt.so's C ABI. This is REFERENCE-SIDE binding code (what a maintainer adds
+// to the reference), kept here so that it is compiled against the reference's own headers and run (oracle/Makefile target
+// `dropin`, tests/test_dropin_gpu.py). It is not part of the product library.
+#include <vector_types.h>   // uchar4 (the reference gets it through its CUDA includes)
+#include "pathtrace.h"
+#include "scene.h"
+#include <kdpt.h>
+#include <cstdio>
+#include <cstring>
+
+static kdpt_ctx* g_ctx = nullptr;
+static Scene* g_scene = nullptr;
+
+void pathtraceInit(Scene* scene, bool /*enablekd*/) {                       // pathtrace.cu:201-272
+    g_scene = scene;
+    kdpt_scene s{};
+    s.nodes = (const kdpt_node_bare*)scene->newNodesBare;     s.numNodes = scene->hasObj ? scene->numNodes : 0;
+    s.tris  = (const kdpt_tri_bare*)scene->newTrianglesBare;  s.numTris  = scene->hasObj ? scene->numTriangles : 0;
+    s.geoms = (const kdpt_geom*)scene->geoms.data();          s.numGeoms = (int)scene->geoms.size();
+    s.materials = (const kdpt_material*)scene->materials.data(); s.numMaterials = (int)scene->materials.size();
+    s.objMaterialOffsets = scene->obj_materialOffsets;        s.numShapes = scene->obj_numshapes;
+    std::memcpy(&s.camera, &scene->state.camera, sizeof(kdpt_camera));       // already recomputed by runCuda()
+    s.traceDepth = scene->state.traceDepth;
+    if (kdpt_create(&s, /*device*/0, &g_ctx) != KDPT_OK) std::fprintf(stderr, "kdpt: %s\n", kdpt_last_error());
+}
+
+void pathtraceFree(Scene*, bool) { kdpt_destroy(g_ctx); g_ctx = nullptr; }   // pathtrace.cu:274-313
+
+void pathtrace(uchar4* /*pbo*/, int /*frame*/, int iter, float focalLength, float dofAngle, bool /*cacherays*/,
+               bool antialias, float softness, bool enableSss, bool testingmode, bool compaction, bool /*enablekd*/,
+               bool /*vizkd*/, bool /*usebbox*/, bool shortstack) {          // pathtrace.cu:2405-2635
+    kdpt_params p{};
+    p.focalLength = focalLength; p.dofAngle = dofAngle; p.softness = softness;
+    p.antialias = antialias; p.enableSss = enableSss; p.compaction = compaction; p.testingmode = testingmode;
+    p.mode = shortstack ? KDPT_REF_T2 : KDPT_REF_T1;       // bit-compatible with traverseKDbare(ShortHybrid);
+                                                           // KDPT_SHORTSTACK / KDPT_FULLSTACK give the exact closest hit
+    p.sortByMaterial = 1;                                  // the reference sorts in iteration 2 only
+    kdpt_render_stats st;
+    if (kdpt_render(g_ctx, iter, 1, 1, &p, &st) != KDPT_OK) std::fprintf(stderr, "kdpt: %s\n", kdpt_last_error());
+    if (testingmode) std::printf("   pathTrace time = %f\n", st.intersectMs);
+    kdpt_get_image(g_ctx, (float*)g_scene->state.image.data());             // pathtrace.cu:2631-2632
+}

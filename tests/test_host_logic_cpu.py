@@ -131,6 +131,19 @@ def test_gpu_kd_build_fails_loudly_without_a_gpu():
         kdpt.Scene.from_triangles_gpu(np.zeros((4, 18), 'f4'))
 
 
+def test_integration_doc_matches_the_compiled_binding():
+    """INTEGRATION.md's shim is the file that oracle/Makefile compiles against the reference (oracle/dropin/)"""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("```cpp") + 6:]
+    block = block[:block.index("```")]
+    src = open(os.path.join(ROOT, "oracle", "dropin", "pathtrace_kdpt.cpp")).read()
+
+    def code(text):
+        lines = [l.rstrip() for l in text.splitlines()]
+        return [l for l in lines if l.strip() and not l.lstrip().startswith("// ")]
+    assert code(block) == code(src)
+
+
 def test_product_never_touches_the_oracle():
     """no file of the product (package, csrc, include) includes, links, loads or imports anything under oracle/
     (comments may cite it)"""
