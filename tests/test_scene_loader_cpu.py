@@ -149,3 +149,22 @@ def test_loader_equals_the_reference_loader_on_every_bundled_obj(obj):
         assert "fewer normals than vertices" in line, line
     else:
         assert line.endswith("ALL EQUAL"), line
+
+
+def _reference_scenes():
+    d = "/root/reference/scenes"
+    return sorted(f for f in os.listdir(d) if f.endswith(".txt")) if os.path.isdir(d) else []
+
+
+@pytest.mark.parametrize("txt", _reference_scenes() or ["(no reference checkout)"])
+def test_loader_equals_the_reference_loader_on_every_bundled_scene_file(txt):
+    """every scenes/*.txt the reference ships (2-12 materials, cubes and spheres, all camera blocks) through both loaders"""
+    import subprocess, sys
+    from conftest import ROOT
+    ref = "/root/reference/scenes"
+    if not os.path.isdir(ref) or not os.path.exists(os.path.join(ROOT, "oracle/_ref/libkdref.so")):
+        pytest.skip("needs /root/reference and oracle/_ref/libkdref.so")
+    r = subprocess.run([sys.executable, os.path.join(GOLDEN, "compare_loader.py"), os.path.join(ref, txt), os.path.join(ref, "sphere_low_1.obj")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout.strip().splitlines()[-1].endswith("ALL EQUAL"), r.stdout[-300:]
