@@ -9,7 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-SCENE_FILES = ["cornell_sphere_low_1.npz", "cornell8_stanford_bunny.npz", "cornell_dragon_5.npz"]
+SCENE_FILES = ["cornell_sphere_low_1.npz", "cornell8_stanford_bunny.npz", "cornell_dragon_5.npz",
+               "cornell_chair.npz", "cornell_hazelnut.npz"]      # chair: two OBJ shapes
 
 
 def pytest_configure(config):

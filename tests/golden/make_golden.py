@@ -23,7 +23,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
 SCENES = [("cornell.txt", "sphere_low_1.obj", "cornell_sphere_low_1.npz", 4000),
           ("cornell8.txt", "stanford_bunny.obj", "cornell8_stanford_bunny.npz", 4000),
-          ("cornell.txt", "dragon_5.obj", "cornell_dragon_5.npz", 3000)]
+          ("cornell.txt", "dragon_5.obj", "cornell_dragon_5.npz", 3000),
+          ("cornell.txt", "chair.obj", "cornell_chair.npz", 2000),          # two OBJ shapes
+          ("cornell.txt", "hazelnut.obj", "cornell_hazelnut.npz", 2000)]
 
 NODE = np.dtype([('axis', 'i4'), ('splitPos', 'f4'), ('mins', 'f4', 3), ('maxs', 'f4', 3), ('ID', 'i4'), ('parentID', 'i4'),
                  ('leftID', 'i4'), ('rightID', 'i4'), ('triIdStart', 'i4'), ('triIdSize', 'i4'), ('tmin', 'f4'), ('tmax', 'f4')])
