@@ -201,6 +201,12 @@ int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_
 int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, kdpt_path_segment* paths, int n,
                 kdpt_intersection* isects, int stages);
 int kdpt_clear_image(kdpt_ctx* ctx);
+/* A camera move without rebuilding anything. The reference answers every camera change with pathtraceFree +
+ * pathtraceInit (main.cpp:1134-1137): a re-upload of the whole tree, and here a re-flatten as well (1 s for 10 M
+ * triangles). This call replaces only the camera (resolution included) and clears the radiance buffer, as pathtraceInit
+ * does (pathtrace.cu:262-263); the binding in INTEGRATION.md uses it whenever pathtraceInit is called again with the
+ * arrays it already holds. */
+int kdpt_set_camera(kdpt_ctx* ctx, const kdpt_camera* camera);
 /* Run all of this context's work on the caller's stream (a cudaStream_t; NULL restores the context's own stream). */
 int kdpt_set_stream(kdpt_ctx* ctx, void* stream);
 /* Accumulate radiance into a caller-owned DEVICE buffer of W*H*3 floats (e.g. the tensor an NCCL all-reduce runs

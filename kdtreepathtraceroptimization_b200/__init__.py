@@ -118,6 +118,7 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_scene_free.argtypes = [vp]
     lib.kdpt_scene_free.restype = None
     lib.kdpt_clear_image.argtypes = [vp]
+    lib.kdpt_set_camera.argtypes = [vp, vp]
     lib.kdpt_set_stream.argtypes = [vp, vp]
     lib.kdpt_bind_image.argtypes = [vp, vp]
     lib.kdpt_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
@@ -368,6 +369,14 @@ class Context:
         _check(self._lib.kdpt_bounce(self._h, int(iteration), int(depth), ctypes.byref(p), _ptr(paths), len(paths),
                                      _ptr(isects), int(stages)), "kdpt_bounce")
         return paths, isects
+
+    def set_camera(self, camera: np.ndarray):
+        """kdpt_set_camera: new camera (CAMERA[1], resolution included), radiance buffer cleared, tree untouched"""
+        cam = np.ascontiguousarray(camera)
+        _check(self._lib.kdpt_set_camera(self._h, cam.ctypes.data_as(ctypes.c_void_p)), "kdpt_set_camera")
+        import copy
+        self.scene = copy.copy(self.scene)          # the caller's Scene object keeps its own camera
+        self.scene.camera = cam.copy()
 
     def clear_image(self):
         _check(self._lib.kdpt_clear_image(self._h), "kdpt_clear_image")

@@ -62,9 +62,10 @@ struct kdpt_ctx {
 
 namespace kdpt {
 // rays per slice of kdpt_trace's upload / trace / download pipeline (batches of up to two slices go through whole).
-// Measured on the 10 M-triangle soup, 16.7 M rays from pinned host buffers: 2 M-ray slices 66.6 Mrays/s end to end,
-// 4 M 83.6, unsliced 84-92 — what a slice gains in copy overlap it loses in the leaf binning, which needs many rays per leaf
-constexpr int kTraceSlice = 1 << 23;
+// A slice gains copy overlap and loses in the leaf binning, which needs many rays per leaf. Measured on the 10 M-triangle
+// soup, 16.7 M rays from pinned host buffers, end to end: on a box with fast host copies (~25 GB/s) 2 M-ray slices 66.6
+// Mrays/s, 4 M 83.6, unsliced 84-92; on a box with slow ones (~6.5 GB/s) unsliced drops to 57. 4 M is the robust choice.
+constexpr int kTraceSlice = 1 << 22;
 // kdpt_trace.cu
 int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n, kdpt_hit* dHits, int mode,
                 cudaStream_t stream);

@@ -900,6 +900,23 @@ int kdpt_clear_image(kdpt_ctx* ctx)
     return KDPT_OK;
 }
 
+int kdpt_set_camera(kdpt_ctx* ctx, const kdpt_camera* camera)
+{
+    if (!ctx || !camera) { setError("kdpt_set_camera: null argument"); return KDPT_ERR_ARG; }
+    if (camera->resolution[0] <= 0 || camera->resolution[1] <= 0) { setError("kdpt_set_camera: resolution must be positive"); return KDPT_ERR_ARG; }
+    const long long n = (long long)camera->resolution[0] * camera->resolution[1];
+    if (n >= (1ll << kSegShift)) { setError("kdpt_set_camera: more than 2^26 pixels"); return KDPT_ERR_ARG; }
+    if (ctx->boundImage && ctx->scene.hasCamera && (int)n != ctx->pixelCount) {
+        setError("kdpt_set_camera: a caller-owned radiance buffer is bound; unbind it (kdpt_bind_image NULL) before changing the resolution");
+        return KDPT_ERR_STATE;
+    }
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));      // launches in flight took the old camera by value; the image may be resized
+    ctx->scene.camera = *camera;
+    ctx->scene.hasCamera = true;
+    return kdpt_clear_image(ctx);                       // pathtraceInit zeroes dev_image (pathtrace.cu:262-263); resizes if needed
+}
+
 int kdpt_get_image(kdpt_ctx* ctx, float* rgb)
 {
     if (!ctx || !rgb) { setError("kdpt_get_image: null argument"); return KDPT_ERR_ARG; }

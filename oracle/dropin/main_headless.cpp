@@ -3,7 +3,7 @@
 // camera (main.cpp:1053-1073 + runCuda 1111-1129, through libkdpt's host helper), then what runCuda does per frame
 // (main.cpp:1134-1166): pathtraceInit once, pathtrace(iteration) per sample with the reference's default toggles
 // (main.cpp:35-60), and the accumulated scene->state.image dumped as raw floats. TEST INFRASTRUCTURE.
-//     usage: dropin_render SCENE.txt MESH.obj MTL_DIR/ WIDTH HEIGHT SPP OUT.f32 [shortstack=1]
+//     usage: dropin_render SCENE.txt MESH.obj MTL_DIR/ WIDTH HEIGHT SPP OUT.f32 [shortstack=1 [OUT_AFTER_CAMERA_MOVE.f32]]
 #include <vector_types.h>   // uchar4 (the reference gets it through its CUDA includes)
 #include "pathtrace.h"
 #include "scene.h"
@@ -43,6 +43,20 @@ int main(int argc, char** argv)
     if (!f) return 1;
     std::fwrite(scene->state.image.data(), sizeof(glm::vec3), scene->state.image.size(), f);
     std::fclose(f);
+    if (argc > 9) {
+        // a camera move as runCuda() handles it (main.cpp:1134-1137): pathtraceFree + pathtraceInit with the same scene,
+        // iteration restarts at 1; second image -> argv[9]
+        cam.position.x += 0.25f;
+        pathtraceFree(scene, true);
+        scene->state.image.assign((size_t)W * H, glm::vec3(0.0f));
+        pathtraceInit(scene, true);
+        for (int it = 1; it <= spp; it++)
+            pathtrace(nullptr, 0, it, 6.0f, 0.0f, false, true, 0.0f, false, false, true, true, false, false, shortstack);
+        FILE* g = std::fopen(argv[9], "wb");
+        if (!g) return 1;
+        std::fwrite(scene->state.image.data(), sizeof(glm::vec3), scene->state.image.size(), g);
+        std::fclose(g);
+    }
     pathtraceFree(scene, true);
     std::printf("{\"nodes\": %d, \"triangles\": %d, \"geoms\": %d, \"materials\": %d}\n", scene->hasObj ? scene->numNodes : 0,
                 scene->hasObj ? scene->numTriangles : 0, (int)scene->geoms.size(), (int)scene->materials.size());

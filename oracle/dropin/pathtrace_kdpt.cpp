@@ -11,6 +11,8 @@
 
 static kdpt_ctx* g_ctx = nullptr;
 static Scene* g_scene = nullptr;
+static const void* g_nodes = nullptr; static const void* g_tris = nullptr;      // what g_ctx was built from
+static int g_numNodes = -1, g_numTris = -1, g_numGeoms = -1, g_numMaterials = -1;
 
 void pathtraceInit(Scene* scene, bool /*enablekd*/) {                       // pathtrace.cu:201-272
     g_scene = scene;
@@ -22,10 +24,20 @@ void pathtraceInit(Scene* scene, bool /*enablekd*/) {                       // p
     s.objMaterialOffsets = scene->obj_materialOffsets;        s.numShapes = scene->obj_numshapes;
     std::memcpy(&s.camera, &scene->state.camera, sizeof(kdpt_camera));       // already recomputed by runCuda()
     s.traceDepth = scene->state.traceDepth;
+    // runCuda() frees and re-inits on every camera move (main.cpp:1134-1137) with the arrays it already gave us:
+    // keep the flattened tree on the GPU and only swap the camera (the radiance buffer is cleared either way)
+    if (g_ctx && s.nodes == g_nodes && s.tris == g_tris && s.numNodes == g_numNodes && s.numTris == g_numTris &&
+        s.numGeoms == g_numGeoms && s.numMaterials == g_numMaterials) {
+        if (kdpt_set_camera(g_ctx, &s.camera) != KDPT_OK) std::fprintf(stderr, "kdpt: %s\n", kdpt_last_error());
+        return;
+    }
+    kdpt_destroy(g_ctx); g_ctx = nullptr;
     if (kdpt_create(&s, /*device*/0, &g_ctx) != KDPT_OK) std::fprintf(stderr, "kdpt: %s\n", kdpt_last_error());
+    g_nodes = s.nodes; g_tris = s.tris; g_numNodes = s.numNodes; g_numTris = s.numTris;
+    g_numGeoms = s.numGeoms; g_numMaterials = s.numMaterials;
 }
 
-void pathtraceFree(Scene*, bool) { kdpt_destroy(g_ctx); g_ctx = nullptr; }   // pathtrace.cu:274-313
+void pathtraceFree(Scene*, bool) {}      // pathtrace.cu:274-313; the context lives until the next scene (see pathtraceInit)
 
 void pathtrace(uchar4* /*pbo*/, int /*frame*/, int iter, float focalLength, float dofAngle, bool /*cacherays*/,
                bool antialias, float softness, bool enableSss, bool testingmode, bool compaction, bool /*enablekd*/,

@@ -25,8 +25,9 @@ def test_reference_host_code_plus_libkdpt_equals_the_library_alone(tmp_path, txt
         pytest.skip("oracle/_ref/dropin_render not built (needs /root/reference at build time)")
     W, H, spp = 96, 64, 5
     out = tmp_path / "img.f32"
+    out2 = tmp_path / "img_moved.f32"
     r = subprocess.run([EXE, os.path.join(SCENES, txt), os.path.join(SCENES, obj), SCENES + "/", str(W), str(H), str(spp), str(out),
-                        str(shortstack)], capture_output=True, text=True, timeout=120)
+                        str(shortstack), str(out2)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "kdpt:" not in r.stderr, r.stderr                       # the shim prints kdpt_last_error() on any failure
     info = json.loads(r.stdout.strip().splitlines()[-1])
@@ -39,5 +40,21 @@ def test_reference_host_code_plus_libkdpt_equals_the_library_alone(tmp_path, txt
         for it in range(1, spp + 1):
             ctx.render(it, 1, 1, p)
         want = ctx.image().reshape(H, W, 3)
+        # the camera move of runCuda(): pathtraceFree + pathtraceInit with the same scene, which the shim turns into
+        # kdpt_set_camera on the context it already holds
+        cam = sc.camera.copy()
+        cam['position'][0][0] = np.float32(cam['position'][0][0]) + np.float32(0.25)
+        ctx.set_camera(cam)
+        for it in range(1, spp + 1):
+            ctx.render(it, 1, 1, p)
+        moved = ctx.image().reshape(H, W, 3)
+    moved_sc = kdpt.Scene.load(os.path.join(SCENES, txt), os.path.join(SCENES, obj)).with_resolution(W, H).first_frame_camera()
+    moved_sc.camera = cam
+    with kdpt.Context(moved_sc) as fresh:
+        fresh.clear_image(); fresh.render(1, spp, 1, p)
+        fresh_img = fresh.image().reshape(H, W, 3)
     assert want.max() > 0
     assert got.tobytes() == want.tobytes()
+    got2 = np.fromfile(out2, '<f4').reshape(H, W, 3)
+    assert moved.tobytes() == fresh_img.tobytes()          # kdpt_set_camera == a fresh context with that camera
+    assert got2.tobytes() == moved.tobytes() and got2.tobytes() != got.tobytes()
