@@ -103,29 +103,72 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
     unsigned hwc = std::thread::hardware_concurrency();
     const int nthreads = numTris < (1 << 16) ? 1 : (int)(hwc == 0 ? 4 : (hwc > 32 ? 32 : hwc));
     {
-        // sharded by hash so that every shard is built by one thread scanning in index order (first occurrence wins)
-        std::vector<uint64_t> hashes((size_t)numTris);
-        auto hashRange = [&](int lo, int hi) {
-            TriKeyHash H;
-            for (int i = lo; i < hi; i++) { TriKey k; memcpy(k.w, &tris[i], sizeof k.w); hashes[i] = (uint64_t)H(k); }
-        };
-        auto shard = [&](int t) {
-            std::unordered_map<TriKey, int, TriKeyHash> first;
-            first.reserve((size_t)numTris / nthreads + 16);
-            for (int i = 0; i < numTris; i++) {
-                if ((int)((hashes[i] >> 20) % (uint64_t)nthreads) != t) continue;
-                TriKey k; memcpy(k.w, &tris[i], sizeof k.w);
-                auto it = first.find(k);
-                if (it == first.end()) { first.emplace(k, i); canon[i] = i; } else canon[i] = it->second;
+        // Sort-based, cache-friendly and parallel (a hash map of 76-byte keys costs a few cache misses per entry — it
+        // was most of pathtraceInit on the multi-million-triangle scenes): entries are keyed by a 64-bit hash of their
+        // 76 bytes, partitioned by the top hash bits, each part sorted by (hash, index); inside a run of equal hashes
+        // the smallest index whose bytes match is the canonical one (runs are almost always one distinct triangle;
+        // true hash collisions are resolved by comparing against the run's earlier distinct heads).
+        struct HashIdx { uint64_t h; int i; };
+        std::vector<HashIdx> keys((size_t)numTris);
+        const int parts = nthreads == 1 ? 1 : nthreads * 8;
+        std::vector<size_t> partBegin((size_t)parts + 1, 0);
+        auto partOf = [&](uint64_t h) { return (int)(((h >> 32) * (uint64_t)parts) >> 32); };
+        auto canonPart = [&](size_t lo, size_t hi) {
+            std::sort(keys.begin() + lo, keys.begin() + hi, [](const HashIdx& x, const HashIdx& y) { return x.h != y.h ? x.h < y.h : x.i < y.i; });
+            size_t r = lo;
+            while (r < hi) {
+                size_t e = r + 1;
+                while (e < hi && keys[e].h == keys[r].h) e++;
+                // run [r, e): heads = distinct contents seen so far in this run, in index order
+                int headsInline[4]; int numHeads = 0; std::vector<int> headsMore;
+                for (size_t k = r; k < e; k++) {
+                    const int i = keys[k].i;
+                    int found = -1;
+                    for (int q = 0; q < numHeads && found < 0; q++) {
+                        const int hd = q < 4 ? headsInline[q] : headsMore[q - 4];
+                        if (memcmp(&tris[hd], &tris[i], sizeof(kdpt_tri_bare)) == 0) found = hd;
+                    }
+                    if (found < 0) { found = i; if (numHeads < 4) headsInline[numHeads] = i; else headsMore.push_back(i); numHeads++; }
+                    canon[i] = found;
+                }
+                r = e;
             }
         };
-        if (nthreads == 1) { hashRange(0, numTris); shard(0); }
-        else {
+        if (nthreads == 1) {
+            TriKeyHash H;
+            for (int i = 0; i < numTris; i++) { TriKey k; memcpy(k.w, &tris[i], sizeof k.w); keys[i] = HashIdx{(uint64_t)H(k), i}; }
+            canonPart(0, (size_t)numTris);
+        } else {
+            // pass 1: hash + per-thread part counts; pass 2: stable scatter into parts; pass 3: sort + resolve parts
+            std::vector<uint64_t> hashes((size_t)numTris);
+            std::vector<std::vector<size_t>> counts((size_t)nthreads, std::vector<size_t>((size_t)parts, 0));
+            auto range = [&](int t, int& lo, int& hi) { lo = (int)((long long)numTris * t / nthreads); hi = (int)((long long)numTris * (t + 1) / nthreads); };
             std::vector<std::thread> th;
-            for (int t = 0; t < nthreads; t++) th.emplace_back(hashRange, (int)((long long)numTris * t / nthreads), (int)((long long)numTris * (t + 1) / nthreads));
+            for (int t = 0; t < nthreads; t++)
+                th.emplace_back([&, t]() {
+                    int lo, hi; range(t, lo, hi);
+                    TriKeyHash H;
+                    for (int i = lo; i < hi; i++) { TriKey k; memcpy(k.w, &tris[i], sizeof k.w); hashes[i] = (uint64_t)H(k); counts[t][partOf(hashes[i])]++; }
+                });
             for (auto& t : th) t.join();
             th.clear();
-            for (int t = 0; t < nthreads; t++) th.emplace_back(shard, t);
+            std::vector<std::vector<size_t>> offs((size_t)nthreads, std::vector<size_t>((size_t)parts, 0));
+            size_t acc = 0;
+            for (int p = 0; p < parts; p++) {
+                partBegin[p] = acc;
+                for (int t = 0; t < nthreads; t++) { offs[t][p] = acc; acc += counts[t][p]; }
+            }
+            partBegin[parts] = acc;
+            for (int t = 0; t < nthreads; t++)
+                th.emplace_back([&, t]() {
+                    int lo, hi; range(t, lo, hi);
+                    for (int i = lo; i < hi; i++) keys[offs[t][partOf(hashes[i])]++] = HashIdx{hashes[i], i};
+                });
+            for (auto& t : th) t.join();
+            th.clear();
+            std::atomic<int> nextPart(0);
+            for (int t = 0; t < nthreads; t++)
+                th.emplace_back([&]() { for (int p = nextPart.fetch_add(1); p < parts; p = nextPart.fetch_add(1)) canonPart(partBegin[p], partBegin[p + 1]); });
             for (auto& t : th) t.join();
         }
     }

@@ -4,6 +4,7 @@
 #include "../../kdtreepathtraceroptimization_b200/csrc/kdpt_core.cuh"
 #include "../../kdtreepathtraceroptimization_b200/csrc/kdpt_flatten.h"
 #include <string>
+#include <string.h>
 
 using namespace kdpt;
 
@@ -46,5 +47,14 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
         hits[i].normal[0] = H.nx; hits[i].normal[1] = H.ny; hits[i].normal[2] = H.nz;
     }
     if (counters) { counters[0] = cn; counters[1] = cl; counters[2] = ct; }
+    return 0;
+}
+
+// canonical index of every TriBare entry as the product's flatten computes it (what kdpt_hit.tri reports)
+extern "C" int hostsim_canonical(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, int* canonOut)
+{
+    FlatTree F; std::string err;
+    if (!flatten(nodes, numNodes, tris, numTris, F, err)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+    for (int i = 0; i < numTris; i++) { int c; memcpy(&c, &F.triC[i].y, 4); canonOut[F.triOrig[i]] = c; }
     return 0;
 }

@@ -131,6 +131,22 @@ def test_gpu_kd_build_fails_loudly_without_a_gpu():
         kdpt.Scene.from_triangles_gpu(np.zeros((4, 18), 'f4'))
 
 
+def test_canonical_index_of_a_large_tree_with_duplicate_triangles(hostsim):
+    """flatten's canonical index (first TriBare entry with identical 76 bytes) on a tree big enough for its partitioned,
+    multi-threaded path, with a tenth of the input triangles duplicated byte for byte under other source indices"""
+    from kdtreepathtraceroptimization_b200 import meshes
+    from conftest import P, canonical_index
+    t18 = meshes.triangle_soup(200_000, seed=5, edge=0.02)
+    t18[-20_000:] = t18[:20_000]
+    sc = kdpt.Scene.from_triangles(t18)
+    assert len(sc.tris) >= 1 << 16
+    got = np.zeros(len(sc.tris), 'i4')
+    assert hostsim.hostsim_canonical(P(sc.nodes), len(sc.nodes), P(sc.tris), len(sc.tris), P(got)) == 0
+    want = canonical_index(sc.tris)
+    assert (want != np.arange(len(want))).sum() > 20_000         # duplicates across leaves and across sources
+    assert (got == want).all()
+
+
 def test_integration_doc_matches_the_compiled_binding():
     """INTEGRATION.md's shim is the file that oracle/Makefile compiles against the reference (oracle/dropin/)"""
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
