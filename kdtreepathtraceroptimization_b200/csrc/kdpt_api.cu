@@ -56,8 +56,8 @@ void DeviceBuffer::release()
     p = nullptr; bytes = 0;
 }
 
-template <class T>
-static int upload(DeviceBuffer& buf, const std::vector<T>& v, const T** devPtr, cudaStream_t s)
+template <class V, class T = typename V::value_type>
+static int upload(DeviceBuffer& buf, const V& v, const T** devPtr, cudaStream_t s)
 {
     int rc = buf.alloc(v.size() * sizeof(T));
     if (rc) return rc;

@@ -276,7 +276,7 @@ struct Scope {               // frees every device buffer of the build on every 
 } // namespace
 
 int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int device,
-                    std::vector<kdpt_node_bare>& outNodes, std::vector<kdpt_tri_bare>& outTris, std::vector<int>& outSource,
+                    std::vector<kdpt_node_bare>& outNodes, BulkVector<kdpt_tri_bare>& outTris, BulkVector<int>& outSource,
                     float* deviceMs)
 {
     int count = 0;

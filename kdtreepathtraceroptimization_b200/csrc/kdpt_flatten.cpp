@@ -109,7 +109,7 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
         // the smallest index whose bytes match is the canonical one (runs are almost always one distinct triangle;
         // true hash collisions are resolved by comparing against the run's earlier distinct heads).
         struct HashIdx { uint64_t h; int i; };
-        std::vector<HashIdx> keys((size_t)numTris);
+        BulkVector<HashIdx> keys((size_t)numTris);
         const int parts = nthreads == 1 ? 1 : nthreads * 8;
         std::vector<size_t> partBegin((size_t)parts + 1, 0);
         auto partOf = [&](uint64_t h) { return (int)(((h >> 32) * (uint64_t)parts) >> 32); };
@@ -140,7 +140,7 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
             canonPart(0, (size_t)numTris);
         } else {
             // pass 1: hash + per-thread part counts; pass 2: stable scatter into parts; pass 3: sort + resolve parts
-            std::vector<uint64_t> hashes((size_t)numTris);
+            BulkVector<uint64_t> hashes((size_t)numTris);
             std::vector<std::vector<size_t>> counts((size_t)nthreads, std::vector<size_t>((size_t)parts, 0));
             auto range = [&](int t, int& lo, int& hi) { lo = (int)((long long)numTris * t / nthreads); hi = (int)((long long)numTris * (t + 1) / nthreads); };
             std::vector<std::thread> th;

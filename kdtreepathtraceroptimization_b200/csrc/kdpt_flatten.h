@@ -2,9 +2,13 @@
 // device layout described in kdpt_core.cuh. Pure host C++, no CUDA.
 #pragma once
 #include <stdint.h>
+#include <memory>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/kdpt.h"
+#include "kdpt_bulk.h"
 
 namespace kdpt {
 
@@ -15,9 +19,9 @@ struct HostF2 { float x, y; };
 struct FlatTree {
     std::vector<HostNode> nodes;
     std::vector<HostF4> boxLo, boxHi;
-    std::vector<HostF4> triA, triB, nrmA, nrmB;
-    std::vector<HostF2> triC, nrmC;
-    std::vector<int> triOrig;                   // TriBare index of every (possibly reordered) leaf entry
+    BulkVector<HostF4> triA, triB, nrmA, nrmB;
+    BulkVector<HostF2> triC, nrmC;
+    BulkVector<int> triOrig;                    // TriBare index of every (possibly reordered) leaf entry
     std::vector<HostF4> chunkLo, chunkHi;       // padded AABB of every 32-triangle chunk of the chunked leaves
     std::vector<HostF4> superLo, superHi;       // AABB of every group of 32 chunks of the very fat leaves
     int numChunks = 0;

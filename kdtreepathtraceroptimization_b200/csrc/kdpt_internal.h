@@ -72,6 +72,6 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
 // kdpt_build.cu — KD build on the GPU; same arrays as kdpt_scene.cpp:buildTree. deviceMs (may be NULL): device time from
 // the end of the triangle upload to the last kernel, including the per-level host decisions
 int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int device,
-                    std::vector<kdpt_node_bare>& nodes, std::vector<kdpt_tri_bare>& tris, std::vector<int>& triSource,
+                    std::vector<kdpt_node_bare>& nodes, kdpt::BulkVector<kdpt_tri_bare>& tris, kdpt::BulkVector<int>& triSource,
                     float* deviceMs);
 } // namespace kdpt

@@ -11,6 +11,7 @@
 // parser (tryParseDouble: it is NOT correctly rounded, so strtod would give different vertices), KDnode's
 // float/double mix in the split predicate.
 #include "../../include/kdpt.h"
+#include "kdpt_bulk.h"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +27,7 @@ namespace kdpt {
 void setError(const std::string& msg);
 // kdpt_build.cu: the same build, level-synchronous on the GPU
 int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int device, std::vector<kdpt_node_bare>& nodes,
-                    std::vector<kdpt_tri_bare>& tris, std::vector<int>& triSource, float* deviceMs);
+                    kdpt::BulkVector<kdpt_tri_bare>& tris, kdpt::BulkVector<int>& triSource, float* deviceMs);
 }
 
 namespace {
@@ -441,8 +442,8 @@ struct Builder {
 
 struct HostScene {
     std::vector<kdpt_node_bare> nodes;
-    std::vector<kdpt_tri_bare> tris;
-    std::vector<int> triSource;
+    kdpt::BulkVector<kdpt_tri_bare> tris;
+    kdpt::BulkVector<int> triSource;
     std::vector<kdpt_geom> geoms;
     std::vector<kdpt_material> materials;
     std::vector<int> offsets;
@@ -481,15 +482,28 @@ void buildTree(const float* tri18, const int* mtl, int n, int maxdepth, HostScen
     for (int i = 0; i < n; i++) all[i] = i;
     b.split(root, all, 0, center);
     hs.nodes.swap(b.nodes);
-    hs.triSource.swap(b.leafTri);
+    hs.triSource.assign(b.leafTri.begin(), b.leafTri.end());
     hs.tris.resize(hs.triSource.size());
-    for (size_t i = 0; i < hs.triSource.size(); i++) {
-        const float* s = tri18 + 18 * (size_t)hs.triSource[i];
-        kdpt_tri_bare& t = hs.tris[i];
-        t.x1 = s[0]; t.y1 = s[1]; t.z1 = s[2]; t.x2 = s[3]; t.y2 = s[4]; t.z2 = s[5]; t.x3 = s[6]; t.y3 = s[7]; t.z3 = s[8];
-        t.nx1 = s[9]; t.ny1 = s[10]; t.nz1 = s[11]; t.nx2 = s[12]; t.ny2 = s[13]; t.nz2 = s[14];
-        t.nx3 = s[15]; t.ny3 = s[16]; t.nz3 = s[17];
-        t.mtlIdx = mtl ? mtl[hs.triSource[i]] : 0;
+    // cacheTrianglesBare (scene.cpp:934-968): one 76-byte component-major record per leaf entry; entries are independent,
+    // so big trees are filled by all host cores (which then also take the page faults of the ~76 B x entries array)
+    auto fill = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const float* s = tri18 + 18 * (size_t)hs.triSource[i];
+            kdpt_tri_bare& t = hs.tris[i];
+            t.x1 = s[0]; t.y1 = s[1]; t.z1 = s[2]; t.x2 = s[3]; t.y2 = s[4]; t.z2 = s[5]; t.x3 = s[6]; t.y3 = s[7]; t.z3 = s[8];
+            t.nx1 = s[9]; t.ny1 = s[10]; t.nz1 = s[11]; t.nx2 = s[12]; t.ny2 = s[13]; t.nz2 = s[14];
+            t.nx3 = s[15]; t.ny3 = s[16]; t.nz3 = s[17];
+            t.mtlIdx = mtl ? mtl[hs.triSource[i]] : 0;
+        }
+    };
+    const size_t total = hs.triSource.size();
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nt = total < (1u << 17) ? 1 : (int)(hw == 0 ? 4 : (hw > 32 ? 32 : hw));
+    if (nt == 1) fill(0, total);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; k++) th.emplace_back(fill, total * k / nt, total * (k + 1) / nt);
+        for (auto& t : th) t.join();
     }
 }
 
@@ -717,15 +731,15 @@ uint64_t fnv1a(uint64_t h, const void* p, size_t n)
 struct CacheWriter {
     FILE* f; uint64_t h = 1469598103934665603ull; bool ok = true;
     void put(const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) ok = false; h = fnv1a(h, p, n); }
-    template <class T> void vec(const std::vector<T>& v) { put(v.data(), v.size() * sizeof(T)); }
+    template <class V> void vec(const V& v) { put(v.data(), v.size() * sizeof(typename V::value_type)); }
 };
 struct CacheReader {
     FILE* f; uint64_t h = 1469598103934665603ull; bool ok = true;
     void get(void* p, size_t n) { if (n && fread(p, 1, n, f) != n) ok = false; else h = fnv1a(h, p, n); }
-    template <class T> void vec(std::vector<T>& v, uint64_t count, uint64_t limit)
+    template <class V> void vec(V& v, uint64_t count, uint64_t limit)
     {
         if (!ok || count > limit) { ok = false; return; }
-        v.resize((size_t)count); get(v.data(), v.size() * sizeof(T));
+        v.resize((size_t)count); get(v.data(), v.size() * sizeof(typename V::value_type));
     }
 };
 bool readWholeFile(const std::string& path, std::string& out)
