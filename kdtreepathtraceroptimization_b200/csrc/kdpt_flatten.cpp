@@ -9,8 +9,8 @@
 
 namespace kdpt {
 
-static const int kChunkMinLeaf = 128;
-static const int kSuperMinChunks = 64;   // leaves with at least this many chunks (2048 triangles) get a second level   // leaves at least this large get 32-triangle chunks with bounding boxes
+static const int kChunkMinLeaf = 128;     // leaves at least this large get 32-triangle chunks with bounding boxes
+static const int kSuperMinChunks = 64;    // leaves with at least this many chunks (2048 triangles) get a second level
 
 uint64_t FlatTree::bytes() const
 {

@@ -11,12 +11,12 @@ constexpr int kTraceThreads = 128;
 #ifndef KDPT_COOP_MIN
 #define KDPT_COOP_MIN 8
 #endif
-constexpr int kCoopMin = KDPT_COOP_MIN;
+constexpr int kCoopMin = KDPT_COOP_MIN;     // leaves with at least this many triangles may be tested by the whole warp
 #ifndef KDPT_BLOCK_RANGE
 #define KDPT_BLOCK_RANGE 16
 #endif
 constexpr int kBlockRange = KDPT_BLOCK_RANGE;   // packets per block-level ticket of a binned batch (see traceKernel)
-constexpr int kBinMinRays = 1 << 16;     // batches at least this big are traced in leaf order (see binRaysKernel)   // leaves with at least this many triangles are tested by the whole warp
+constexpr int kBinMinRays = 1 << 16;     // batches at least this big are traced in leaf order (see binRaysKernel)
 
 // Persistent threads: a fixed grid (a multiple of the SM count) whose warps pull 32-ray packets from a global
 // counter until the batch is drained, so a warp stuck in a fat leaf does not hold back the rest of its block's
