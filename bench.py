@@ -308,7 +308,7 @@ def run_trace_workload(args):
         dt1, _ = cpu_run(KO_T1, kcpu)
         print(json.dumps({"metric": "Mrays/s (traverse+intersect)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
                           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": {"workload": desc, "rays_per_step_per_gpu": nrays, "tree": ctx.tree_info(),
+                          "data": "synthetic", "config": {"workload": desc, "rays_per_step_per_gpu": nrays, "tree": ctx.tree_info(), "tree_refined": ctx.refined_info(),
                                                           "l2": "working set (tree 0.9 GB + rays/hits 0.9 GB) exceeds L2; no flush"},
                           "clocks": clk, "gpu_launches": int(launches),
                           "e2e": {"value": world * nrays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": nrays * 24, "d2h_bytes_per_step": nrays * 32},
@@ -520,7 +520,7 @@ def main():
                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": desc, "spp_per_step": S, "resolution": [w, h], "trace_depth": sc.trace_depth,
-                          "traversal": mode_name, "parallelism": f"sample-sharded x{world}, tree replicated, "
+                          "traversal": mode_name, "tree": ctx.tree_info(), "tree_refined": ctx.refined_info(), "parallelism": f"sample-sharded x{world}, tree replicated, "
                           "NCCL all-reduce of the radiance buffer per step" if world > 1 else "single GPU",
                           "l2": "flushed between timed steps (256 MiB fill, untimed)"},
                "spp_per_s": S * world * K / (ms * 1e-3),

@@ -174,12 +174,28 @@ void kdpt_scene_free(kdpt_host_scene* scene);
 
 /* pathtraceInit: flatten + upload. device = CUDA ordinal. The host arrays are not retained. */
 int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out);
+/* The same with build options. The exact modes (KDPT_FULLSTACK / KDPT_SHORTSTACK) do not have to walk the reference's
+ * leaves in the reference's order — they return the brute-force closest hit — so for them pathtraceInit splits every
+ * reference leaf of more than refineLeafMax triangles further, inside its own cell (the reference builder stops at depth 14
+ * or when a split keeps all triangles on one side: leaves of hundreds to tens of thousands of triangles). Results do not
+ * depend on these options; the reference-compatible modes always walk the tree as given. NULL = defaults. */
+typedef struct {
+    int refineLeafMax;          /* < 0: default (4); 0: no refinement (exact modes walk the reference tree, fat leaves are
+                                   tested warp-cooperatively through chunk boxes); > 0: leaf size at which splitting stops */
+    float refineTraversalCost;  /* <= 0: default (1.0); cost of one node step relative to one triangle test in the builder's
+                                   surface-area heuristic */
+    int reserved[6];
+} kdpt_build_opts;
+int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts* opts, kdpt_ctx** out);
 /* pathtraceFree */
 int kdpt_destroy(kdpt_ctx* ctx);
 
 /* sizes of the flattened device representation (bytes), for roofline bookkeeping */
 int kdpt_tree_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* maxDepth, int* maxLeaf,
                    uint64_t* deviceBytes);
+
+/* the tree the exact modes walk (== kdpt_tree_info's numbers when refinement is off) */
+int kdpt_refined_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* maxDepth, int* maxLeaf);
 
 /* n rays in, n hits out, HOST buffers (H2D + kernel + D2H). t_min_in may be NULL (FLT_MAX). */
 int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n, kdpt_hit* hits, int mode);

@@ -65,6 +65,10 @@ class CParams(ctypes.Structure):
                 ("laneQueue", ctypes.c_int), ("reserved", ctypes.c_int * 2)]
 
 
+class CBuildOpts(ctypes.Structure):
+    _fields_ = [("refineLeafMax", ctypes.c_int), ("refineTraversalCost", ctypes.c_float), ("reserved", ctypes.c_int * 6)]
+
+
 class CRenderStats(ctypes.Structure):
     _fields_ = [("rayBounces", ctypes.c_uint64), ("launches", ctypes.c_uint64), ("intersectMs", ctypes.c_float),
                 ("totalMs", ctypes.c_float), ("intersectLaunches", ctypes.c_uint64)]
@@ -95,6 +99,8 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_last_error.restype = ctypes.c_char_p
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.kdpt_create.argtypes = [ctypes.POINTER(_CScene), ci, ctypes.POINTER(vp)]
+    lib.kdpt_create_opts.argtypes = [ctypes.POINTER(_CScene), ci, ctypes.POINTER(CBuildOpts), ctypes.POINTER(vp)]
+    lib.kdpt_refined_info.argtypes = [vp] + [ctypes.POINTER(ci)] * 4
     lib.kdpt_destroy.argtypes = [vp]
     lib.kdpt_tree_info.argtypes = [vp] + [ctypes.POINTER(ci)] * 4 + [ctypes.POINTER(ctypes.c_uint64)]
     lib.kdpt_trace.argtypes = [vp, vp, vp, ci, vp, ci]
@@ -259,7 +265,8 @@ def _ptr(a: np.ndarray):
 class Context:
     """kdpt_ctx: pathtraceInit on creation, pathtraceFree on close()."""
 
-    def __init__(self, scene: Scene, device: int = 0):
+    def __init__(self, scene: Scene, device: int = 0, refine_leaf_max: int = -1, refine_traversal_cost: float = 0.0):
+        """refine_leaf_max: kdpt_build_opts.refineLeafMax (-1 default, 0 = the exact modes walk the reference tree)"""
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         self.scene = scene
@@ -275,7 +282,8 @@ class Context:
         cs.objMaterialOffsets, cs.numShapes = _ptr(scene.offsets), len(scene.offsets)
         ctypes.memmove(ctypes.byref(cs.camera), scene.camera.ctypes.data, CAMERA.itemsize)
         cs.traceDepth = int(scene.trace_depth)
-        _check(self._lib.kdpt_create(ctypes.byref(cs), int(device), ctypes.byref(self._h)), "kdpt_create")
+        opts = CBuildOpts(int(refine_leaf_max), float(refine_traversal_cost))
+        _check(self._lib.kdpt_create_opts(ctypes.byref(cs), int(device), ctypes.byref(opts), ctypes.byref(self._h)), "kdpt_create_opts")
         self.device = device
 
     def close(self):
@@ -301,6 +309,12 @@ class Context:
         _check(self._lib.kdpt_tree_info(self._h, *[ctypes.byref(x) for x in v], ctypes.byref(b)), "kdpt_tree_info")
         return dict(num_nodes=v[0].value, num_leaf_tris=v[1].value, max_depth=v[2].value, max_leaf=v[3].value,
                     device_bytes=b.value)
+
+    def refined_info(self) -> dict:
+        """the tree the exact modes walk (kdpt_refined_info)"""
+        v = [ctypes.c_int() for _ in range(4)]
+        _check(self._lib.kdpt_refined_info(self._h, *[ctypes.byref(x) for x in v]), "kdpt_refined_info")
+        return dict(num_nodes=v[0].value, num_leaf_tris=v[1].value, max_depth=v[2].value, max_leaf=v[3].value)
 
     def trace(self, rays: np.ndarray, t_min_in: np.ndarray | None = None, mode: int = FULLSTACK) -> np.ndarray:
         """Host buffers in, host buffers out (H2D + kernel + D2H inside the call). rays: (n,6) float32 or RAY[n]."""

@@ -124,7 +124,9 @@ int kdpt_destroy(kdpt_ctx* ctx)
     return KDPT_OK;
 }
 
-int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
+int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out) { return kdpt_create_opts(scene, device, nullptr, out); }
+
+int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts* bopts, kdpt_ctx** out)
 {
     static_assert(sizeof(kdpt_geom) == 236 && sizeof(kdpt_material) == 56 && sizeof(kdpt_camera) == 84, "reference POD ABI");
     static_assert(sizeof(kdpt_ray) == 24 && sizeof(kdpt_hit) == 32, "kdpt ABI");
@@ -139,7 +141,12 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     }
     if (device < 0 || device >= count) { setError("kdpt_create: device ordinal out of range"); return KDPT_ERR_ARG; }
     FlatTree flat; std::string err;
-    if (!flatten(scene->nodes, scene->numNodes, scene->tris, scene->numTris, flat, err)) { setError(err); return KDPT_ERR_ARG; }
+    FlattenOpts fopts;
+    if (bopts) {
+        if (bopts->refineLeafMax >= 0) fopts.refineLeafMax = bopts->refineLeafMax;
+        if (bopts->refineTraversalCost > 0.0f) fopts.traversalCost = bopts->refineTraversalCost;
+    }
+    if (!flatten(scene->nodes, scene->numNodes, scene->tris, scene->numTris, flat, err, fopts)) { setError(err); return KDPT_ERR_ARG; }
     if (scene->numGeoms < 0 || scene->numMaterials < 0 || scene->numShapes < 0 ||
         (scene->numGeoms > 0 && !scene->geoms) || (scene->numMaterials > 0 && !scene->materials) ||
         (scene->numShapes > 0 && !scene->objMaterialOffsets)) {
@@ -174,7 +181,8 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     if ((rc = upload(ctx->treeMem[11], flat.chunkHi, (const HostF4**)&T.chunkHi, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[12], flat.superLo, (const HostF4**)&T.superLo, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[13], flat.superHi, (const HostF4**)&T.superHi, s))) return fail(rc);
-    T.numNodes = flat.numNodes; T.numTris = flat.numTris;
+    T.entryOf = nullptr;
+    T.numNodes = flat.numNodes; T.numTris = flat.numTris; T.numRefNodes = flat.numNodes;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = flat.rootLo[a]; T.rootHi[a] = flat.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = flat.tagCand[k];
     T.materialSize = scene->numMaterials;
@@ -183,6 +191,23 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     { size_t hot = (size_t)flat.numTris * 40; T.laneCost32 = hot > ((size_t)4 << 20) ? 192 : (hot > ((size_t)512 << 10) ? 64 : 32); }
     if (const char* e = getenv("KDPT_LANE_COST32")) { int v = atoi(e); if (v > 0) T.laneCost32 = v; }
     ctx->deviceBytes = flat.bytes();
+    // the refined view of the same scene for the exact modes (kdpt_flatten.cpp:refineLeaves)
+    ctx->xtree = T;
+    if (!flat.xnodes.empty()) {
+        Tree& X = ctx->xtree;
+        if ((rc = upload(ctx->treeMem[14], flat.xnodes, (const HostNode**)&X.nodes, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[15], flat.xtriA, (const HostF4**)&X.triA, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[16], flat.xtriB, (const HostF4**)&X.triB, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[17], flat.xtriC, (const HostF2**)&X.triC, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[18], flat.xchunkLo, (const HostF4**)&X.chunkLo, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[19], flat.xchunkHi, (const HostF4**)&X.chunkHi, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[20], flat.xsuperLo, (const HostF4**)&X.superLo, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[21], flat.xsuperHi, (const HostF4**)&X.superHi, s))) return fail(rc);
+        if ((rc = upload(ctx->treeMem[22], flat.entryOf, &X.entryOf, s))) return fail(rc);
+        X.numNodes = (int)flat.xnodes.size(); X.numTris = flat.xNumTris;
+        { size_t hot = (size_t)flat.xNumTris * 40; X.laneCost32 = hot > ((size_t)4 << 20) ? 192 : (hot > ((size_t)512 << 10) ? 64 : 32); }
+        if (const char* e = getenv("KDPT_LANE_COST32")) { int v = atoi(e); if (v > 0) X.laneCost32 = v; }
+    }
 
     SceneDev& S = ctx->scene;
     S.numGeoms = scene->numGeoms; S.numMaterials = scene->numMaterials; S.numShapes = scene->numShapes;
@@ -231,6 +256,12 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out)
     flat.nrmC.clear(); flat.nrmC.shrink_to_fit(); flat.triOrig.clear(); flat.triOrig.shrink_to_fit();
     flat.chunkLo.clear(); flat.chunkLo.shrink_to_fit(); flat.chunkHi.clear(); flat.chunkHi.shrink_to_fit();
     flat.superLo.clear(); flat.superLo.shrink_to_fit(); flat.superHi.clear(); flat.superHi.shrink_to_fit();
+    ctx->xNumNodes = (int)flat.xnodes.size();
+    flat.xnodes.clear(); flat.xnodes.shrink_to_fit(); flat.xtriA.clear(); flat.xtriA.shrink_to_fit();
+    flat.xtriB.clear(); flat.xtriB.shrink_to_fit(); flat.xtriC.clear(); flat.xtriC.shrink_to_fit();
+    flat.xchunkLo.clear(); flat.xchunkLo.shrink_to_fit(); flat.xchunkHi.clear(); flat.xchunkHi.shrink_to_fit();
+    flat.xsuperLo.clear(); flat.xsuperLo.shrink_to_fit(); flat.xsuperHi.clear(); flat.xsuperHi.shrink_to_fit();
+    flat.entryOf.clear(); flat.entryOf.shrink_to_fit();
     ctx->info = flat;
     *out = ctx;
     return KDPT_OK;
@@ -244,6 +275,17 @@ int kdpt_tree_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* ma
     if (maxDepth) *maxDepth = ctx->info.maxDepth;
     if (maxLeaf) *maxLeaf = ctx->info.maxLeaf;
     if (deviceBytes) *deviceBytes = ctx->deviceBytes;
+    return KDPT_OK;
+}
+
+int kdpt_refined_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* maxDepth, int* maxLeaf)
+{
+    if (!ctx) { setError("kdpt_refined_info: null context"); return KDPT_ERR_ARG; }
+    const bool on = ctx->xNumNodes > 0;
+    if (numNodes) *numNodes = on ? ctx->xNumNodes : ctx->info.numNodes;
+    if (numLeafTris) *numLeafTris = on ? ctx->info.xNumTris : ctx->info.numTris;
+    if (maxDepth) *maxDepth = on ? ctx->info.xMaxDepth : ctx->info.maxDepth;
+    if (maxLeaf) *maxLeaf = on ? ctx->info.xMaxLeaf : ctx->info.maxLeaf;
     return KDPT_OK;
 }
 

@@ -52,6 +52,12 @@ constexpr unsigned kNoChunks = 0xffffffffu;
 //   nrmA[i] = (n1.x, n1.y, n1.z, n2.x)  nrmB[i] = (n2.y, n2.z, n3.x, n3.y)  nrmC[i] = (n3.z, mtlIdx)
 //   with e1 = v1 - v0, e2 = v2 - v0 (the first two operations of glm::intersectRayTriangle, done once).
 // boxes (reference-compatible modes only): boxLo[i] = (mins, 0), boxHi[i] = (maxs, NodeBare.axis as int bits).
+//
+// Two views of one scene share this struct. The REFERENCE view is the tree exactly as the reference built it (the
+// reference-compatible modes depend on its leaves and their order). The REFINED view (exact modes) has every fat
+// reference leaf split further (kdpt_flatten.cpp:refineLeaves): nodes / triA / triB / triC / chunk* point at the
+// refined arrays, whose leaf entries carry the canonical TriBare index; the cold per-triangle data (normals,
+// material) stays in the reference view's arrays and is reached through entryOf[canonical index].
 struct Tree {
     const uint4* nodes;
     const float4* boxLo;
@@ -67,8 +73,10 @@ struct Tree {
     const float4* chunkHi;
     const float4* superLo;   // boxes of groups of 32 chunks (leaves with >= 64 chunks); chunkLo[first].w = first group
     const float4* superHi;
+    const int* entryOf;      // refined view only (else NULL): TriBare index -> entry of nrmA/nrmB/nrmC (see below)
     int numNodes;
     int numTris;
+    int numRefNodes;         // nodes[i], i < numRefNodes, are the reference's nodes (both views)
     float rootLo[3], rootHi[3];
     int tagCand[4];     // nodes[0].leftID, nodes[0].rightID, nodes[1].leftID, nodes[1].rightID (T2 quirk)
     int materialSize;   // hst_scene->materials.size()
@@ -188,6 +196,7 @@ KDPT_HD TriHot loadTri(const Tree& T, int i)
 KDPT_HD bool acceptHit(const Tree& T, int i, int canon, V3 o, V3 d, float u, float v, float z, float eps,
                        int tieKey, int tieBest, Hit& H)
 {
+    if (T.entryOf) i = KDPT_LDG(T.entryOf + canon);     // refined view: i indexed the refined hot arrays
     float4 a = KDPT_LDG(T.nrmA + i), b = KDPT_LDG(T.nrmB + i);
     float2 c = KDPT_LDG(T.nrmC + i);
     V3 n1 = mk(a.x, a.y, a.z), n2 = mk(a.w, b.x, b.y), n3 = mk(b.z, b.w, c.x);

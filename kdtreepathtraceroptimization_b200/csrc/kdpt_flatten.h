@@ -25,15 +25,31 @@ struct FlatTree {
     std::vector<HostF4> chunkLo, chunkHi;       // padded AABB of every 32-triangle chunk of the chunked leaves
     std::vector<HostF4> superLo, superHi;       // AABB of every group of 32 chunks of the very fat leaves
     int numChunks = 0;
+    // Refined tree (exact modes only): the reference tree with every leaf of more than FlattenOpts::refineLeafMax
+    // triangles split further by a surface-area-heuristic KD builder (same 16-byte node record; xnodes[i] mirrors
+    // nodes[i] for i < numNodes, the new nodes follow). Leaf entries are (unique) TriBare indices; normals are found
+    // through entryOf. Empty when refinement is off: the exact modes then walk the reference tree itself.
+    std::vector<HostNode> xnodes;
+    BulkVector<HostF4> xtriA, xtriB;
+    BulkVector<HostF2> xtriC;
+    std::vector<HostF4> xchunkLo, xchunkHi, xsuperLo, xsuperHi;
+    BulkVector<int> entryOf;                    // TriBare index -> entry of triA/.../nrmC holding it (inverse of triOrig)
+    int xNumTris = 0, xMaxDepth = 0, xMaxLeaf = 0;
     float rootLo[3] = {0, 0, 0}, rootHi[3] = {0, 0, 0};
     int tagCand[4] = {-1, -1, -1, -1};
     int numNodes = 0, numTris = 0, maxDepth = 0, maxLeaf = 0;
     uint64_t bytes() const;
 };
 
+struct FlattenOpts {
+    int refineLeafMax = 4;      // leaves with more triangles than this are split further for the exact modes; 0 = off
+    float traversalCost = 1.0f; // SAH: cost of one node step relative to one triangle test
+    FlattenOpts();              // defaults, overridable in development by KDPT_REFINE_LEAF / KDPT_REFINE_CT
+};
+
 // Validates the reference invariants the kernels rely on (index == ID, children in range, both-or-no children,
 // leaf ranges inside [0, numTris), depth <= kMaxDepth) and fills `out`. Returns false with `err` set otherwise.
 bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, FlatTree& out,
-             std::string& err);
+             std::string& err, const FlattenOpts& opts = FlattenOpts());
 
 } // namespace kdpt

@@ -869,9 +869,10 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
     // kdpt_params.laneQueue (0 auto, 1 direct, 2 queued); KDPT_QUEUE=0/1/2 (direct/queued/auto) overrides it in development
     static const int envQueue = getenv("KDPT_QUEUE") ? atoi(getenv("KDPT_QUEUE")) : -1;
     A.queuePolicy = envQueue >= 0 ? envQueue : (p.laneQueue == 1 ? 0 : p.laneQueue == 2 ? 1 : 2);
+    const Tree& TV = (p.mode == KDPT_FULLSTACK || p.mode == KDPT_SHORTSTACK) ? ctx->xtree : ctx->tree;
 #define KDPT_LAUNCH_BOUNCE(M)                                                                                                   \
-    if (gen) bounceKernel<M, true><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, *gen);   \
-    else bounceKernel<M, false><<<grid, kThreads, 0, s>>>(ctx->tree, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, noGen)
+    if (gen) bounceKernel<M, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, *gen);   \
+    else bounceKernel<M, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, noGen)
     switch (p.mode) {
     case KDPT_FULLSTACK: KDPT_LAUNCH_BOUNCE(KDPT_FULLSTACK); break;
     case KDPT_SHORTSTACK: KDPT_LAUNCH_BOUNCE(KDPT_SHORTSTACK); break;

@@ -106,6 +106,7 @@ binRaysKernel(Tree T, const kdpt_ray* __restrict__ rays, int n, unsigned* __rest
         // the point where the ray is when it is first inside the root box, then plain point location
         const float te = t0 > 0.0f ? t0 : 0.0f;
         const V3 p = mk(o.x + d.x * te, o.y + d.y * te, o.z + d.z * te);
+        // (down to the reference's leaf: in the refined view the nodes below it have indices >= numRefNodes)
         for (int level = 0; level < kMaxDepth + 1; level++) {
             const uint4 nd = __ldg(T.nodes + node);
             const unsigned axis = nd.w & 3u;
@@ -113,7 +114,9 @@ binRaysKernel(Tree T, const kdpt_ray* __restrict__ rays, int n, unsigned* __rest
             const float split = __uint_as_float(nd.x);
             const float pc = comp(p, (int)axis), dc = comp(d, (int)axis);
             const bool left = pc < split || (pc == split && dc < 0.0f);
-            node = left ? nd.z : nd.y;
+            const unsigned child = left ? nd.z : nd.y;
+            if (child >= (unsigned)T.numRefNodes) break;
+            node = child;
         }
     }
     const unsigned key = node * 8u + ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
@@ -171,17 +174,19 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
     // bin the batch by starting leaf when it is big enough to fill the machine several times over (below that the
     // three extra launches cost more than they save); KDPT_BIN_RAYS=0/1 forces it off/on in development
     static const int envBin = getenv("KDPT_BIN_RAYS") ? atoi(getenv("KDPT_BIN_RAYS")) : -1;
-    const bool bin = ctx->tree.numNodes > 1 && (envBin >= 0 ? envBin != 0 : n >= kBinMinRays);
+    const bool exact = mode == KDPT_FULLSTACK || mode == KDPT_SHORTSTACK;
+    const Tree& T = exact ? ctx->xtree : ctx->tree;
+    const bool bin = T.numRefNodes > 1 && (envBin >= 0 ? envBin != 0 : n >= kBinMinRays);
     const unsigned* order = nullptr;
     if (bin) {
-        const int bins = ctx->tree.numNodes * 8;
+        const int bins = T.numRefNodes * 8;
         int rc;
         if ((rc = ctx->binTmp.ensure(sizeof(unsigned) * (2 * (size_t)n + (size_t)bins)))) return rc;
         unsigned* keys = ctx->binTmp.as<unsigned>();
         unsigned* ord = keys + n;
         unsigned* hist = ord + n;
         KDPT_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * (size_t)bins, stream));
-        binRaysKernel<<<(n + 255) / 256, 256, 0, stream>>>(ctx->tree, dRays, n, keys, hist);
+        binRaysKernel<<<(n + 255) / 256, 256, 0, stream>>>(T, dRays, n, keys, hist);
         binScanKernel<<<1, 1024, 0, stream>>>(hist, bins);
         binScatterKernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, n, hist, ord);
         ctx->launches += 3;
@@ -194,8 +199,8 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
     int need = (n + kTraceThreads - 1) / kTraceThreads;
     if (grid > need) grid = need;
     switch (mode) {
-    case KDPT_FULLSTACK: traceKernel<KDPT_FULLSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
-    case KDPT_SHORTSTACK: traceKernel<KDPT_SHORTSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
+    case KDPT_FULLSTACK: traceKernel<KDPT_FULLSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
+    case KDPT_SHORTSTACK: traceKernel<KDPT_SHORTSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_REF_T1: traceKernel<KDPT_REF_T1><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_REF_T2: traceKernel<KDPT_REF_T2><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     default: setError("kdpt_trace: unknown mode"); return KDPT_ERR_ARG;

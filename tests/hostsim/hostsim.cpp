@@ -8,13 +8,19 @@
 
 using namespace kdpt;
 
+// refinement of the exact modes' tree: -1 = the product's default, 0 = off (walk the reference tree), n = leaf size
+static int g_refine = -1;
+extern "C" void hostsim_set_refine(int leafMax) { g_refine = leafMax; }
+
 extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris,
                              int materialSize, const kdpt_ray* rays, const float* tMinIn, int n, kdpt_hit* hits,
                              int mode, unsigned long long* counters /* nodes, leaves, tris or NULL */,
                              float* lastBary /* n*3 or NULL, ref modes */)
 {
     FlatTree F; std::string err;
-    if (!flatten(nodes, numNodes, tris, numTris, F, err)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+    FlattenOpts fo;
+    if (g_refine >= 0) fo.refineLeafMax = g_refine;
+    if (!flatten(nodes, numNodes, tris, numTris, F, err, fo)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
     Tree T;
     T.nodes = (const uint4*)F.nodes.data();
     T.boxLo = (const float4*)F.boxLo.data(); T.boxHi = (const float4*)F.boxHi.data();
@@ -22,10 +28,20 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
     T.nrmA = (const float4*)F.nrmA.data(); T.nrmB = (const float4*)F.nrmB.data(); T.nrmC = (const float2*)F.nrmC.data();
     T.triOrig = F.triOrig.data(); T.chunkLo = (const float4*)F.chunkLo.data(); T.chunkHi = (const float4*)F.chunkHi.data();
     T.superLo = (const float4*)F.superLo.data(); T.superHi = (const float4*)F.superHi.data();
-    T.numNodes = F.numNodes; T.numTris = F.numTris;
+    T.entryOf = nullptr;
+    T.numNodes = F.numNodes; T.numTris = F.numTris; T.numRefNodes = F.numNodes;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = F.rootLo[a]; T.rootHi[a] = F.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = F.tagCand[k];
     T.materialSize = materialSize; T.laneCost32 = 32;
+    Tree X = T;         // the refined view the exact modes walk (kdpt_api.cu:kdpt_create_opts does the same on the device)
+    if (!F.xnodes.empty()) {
+        X.nodes = (const uint4*)F.xnodes.data();
+        X.triA = (const float4*)F.xtriA.data(); X.triB = (const float4*)F.xtriB.data(); X.triC = (const float2*)F.xtriC.data();
+        X.chunkLo = (const float4*)F.xchunkLo.data(); X.chunkHi = (const float4*)F.xchunkHi.data();
+        X.superLo = (const float4*)F.xsuperLo.data(); X.superHi = (const float4*)F.xsuperHi.data();
+        X.entryOf = F.entryOf.data();
+        X.numNodes = (int)F.xnodes.size(); X.numTris = F.xNumTris;
+    }
     TraceCounters tc = {0, 0, 0};
     unsigned long long cn = 0, cl = 0, ct = 0;
     for (int i = 0; i < n; i++) {
@@ -35,9 +51,9 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
         Hit H;
         tc.nodes = tc.leaves = tc.tris = 0;
         switch (mode) {
-        case KDPT_FULLSTACK: traceExact<kMaxDepth, true>(T, o, d, tin, 0.00001f, H, &tc); break;
-        case KDPT_SHORTSTACK: traceExact<4, true>(T, o, d, tin, 0.0001f, H, &tc); break;
-        case 100: traceExact<1, true>(T, o, d, tin, 0.0001f, H, &tc); break; // restart stress: 1-entry stack
+        case KDPT_FULLSTACK: traceExact<kMaxDepth, true>(X, o, d, tin, 0.00001f, H, &tc); break;
+        case KDPT_SHORTSTACK: traceExact<4, true>(X, o, d, tin, 0.0001f, H, &tc); break;
+        case 100: traceExact<1, true>(X, o, d, tin, 0.0001f, H, &tc); break; // restart stress: 1-entry stack
         case KDPT_REF_T1: traceRef<false>(T, o, d, tin, H, lastBary ? lastBary + 3 * i : nullptr); break;
         case KDPT_REF_T2: traceRef<true>(T, o, d, tin, H, lastBary ? lastBary + 3 * i : nullptr); break;
         default: return -2;
@@ -47,6 +63,16 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
         hits[i].normal[0] = H.nx; hits[i].normal[1] = H.ny; hits[i].normal[2] = H.nz;
     }
     if (counters) { counters[0] = cn; counters[1] = cl; counters[2] = ct; }
+    return 0;
+}
+
+// shape of the refined tree: nodes, leaf entries, max depth, max leaf
+extern "C" int hostsim_refined_info(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, int leafMax, long long* info)
+{
+    FlatTree F; std::string err;
+    FlattenOpts fo; if (leafMax >= 0) fo.refineLeafMax = leafMax;
+    if (!flatten(nodes, numNodes, tris, numTris, F, err, fo)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+    info[0] = (long long)F.xnodes.size(); info[1] = F.xNumTris; info[2] = F.xMaxDepth; info[3] = F.xMaxLeaf;
     return 0;
 }
 

@@ -12,7 +12,9 @@ import kdtreepathtraceroptimization_b200 as kdpt
 from conftest import (KO_BRUTE_T1, KO_BRUTE_T2, KO_STACK_T1, KO_T1, KO_T2, P, ROOT, assert_hits_equal, bits)
 
 
-def _sim(hostsim, g, mode, tmin=None, nmat=6, rays=None):
+def _sim(hostsim, g, mode, tmin=None, nmat=6, rays=None, refine=-1):
+    """refine: leaf size of the exact modes' refined tree (-1 = the product's default, 0 = walk the reference tree)"""
+    hostsim.hostsim_set_refine(refine)
     rays = g['rays'] if rays is None else rays
     n = len(rays)
     out = np.zeros(n, kdpt.HIT)
@@ -27,9 +29,10 @@ def _sim(hostsim, g, mode, tmin=None, nmat=6, rays=None):
 @pytest.mark.parametrize("mode,omode", [(kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2), (100, KO_BRUTE_T2)])
 def test_exact_modes_equal_brute_force(hostsim, oracle, golden, mode, omode):
     for tm in (None, golden['t_min_in']):
-        k, _, _ = _sim(hostsim, golden, mode, tm)
         o = oracle.trace(omode, golden['nodes'], golden['tris'], golden['rays'], tm, 6)
-        assert_hits_equal(k, o, golden['tris'], f"mode {mode}")
+        for refine in (-1, 0, 1, 16):       # default refinement, the reference tree itself, finest, coarse
+            k, _, _ = _sim(hostsim, golden, mode, tm, refine=refine)
+            assert_hits_equal(k, o, golden['tris'], f"mode {mode} refine {refine}")
 
 
 @pytest.mark.parametrize("mode,omode,name", [(kdpt.REF_T1, KO_T1, "T1"), (kdpt.REF_T2, KO_T2, "T2")])
@@ -47,11 +50,26 @@ def test_ref_modes_equal_reference(hostsim, oracle, golden, mode, omode, name):
 
 def test_counters_match_oracle_stack_traversal(hostsim, oracle, golden):
     """the algorithmic-bytes bookkeeping (V nodes, T triangle tests per ray) is the same on both sides"""
-    _, _, ctr = _sim(hostsim, golden, kdpt.FULLSTACK)
+    _, _, ctr = _sim(hostsim, golden, kdpt.FULLSTACK, refine=0)
     _, oc = oracle.trace(KO_STACK_T1, golden['nodes'], golden['tris'], golden['rays'], None, 6, counters=True)
     assert int(ctr[0]) == int(oc['nodes']) and int(ctr[1]) == int(oc['leaves'])
     # triangles actually tested: never more than the algorithmic count, fewer where chunk boxes cull fat leaves
     assert int(ctr[2]) <= int(oc['tris'])
+    # the refined tree trades node steps for triangle tests
+    _, _, cx = _sim(hostsim, golden, kdpt.FULLSTACK)
+    assert int(cx[0]) >= int(ctr[0]) and int(cx[2]) <= int(ctr[2])
+
+
+def test_refined_tree_shape(hostsim, golden_all):
+    """every fat reference leaf is split until the surface-area heuristic stops paying; depth stays within the per-ray
+    stacks (kMaxDepth = 32)"""
+    for name, g in golden_all.items():
+        info = np.zeros(4, 'i8')
+        assert hostsim.hostsim_refined_info(P(g['nodes']), len(g['nodes']), P(g['tris']), len(g['tris']), -1, P(info)) == 0
+        nodes, entries, depth, leaf = (int(x) for x in info)
+        assert nodes >= len(g['nodes']) and depth <= 31
+        assert leaf <= max(24, int(g['nodes']['triIdSize'].max()) // 8), (name, leaf)
+        assert entries <= 8 * len(g['tris'])
 
 
 def test_degenerate_rays(hostsim, oracle, golden_all):
