@@ -276,7 +276,7 @@ struct RayStack {
     }
 };
 
-struct TraceCounters { unsigned nodes, leaves, tris; };
+struct TraceCounters { unsigned nodes, leaves, tris, boxes, hits; };   // boxes: chunk / group boxes tested; hits: triangles accepted by glm
 
 template <int STACK, bool COUNT>
 KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit& H, TraceCounters* ctr)
@@ -318,7 +318,9 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
                 int b = start, e = start + count;
                 if (nd.z != kNoChunks) {
                     float zl = (H.tri >= 0 ? fminf(H.z, zbound) : zbound) + slack;
+                    if (COUNT && sup0 >= 0 && (c & 31) == 0) ctr->boxes++;
                     if (sup0 >= 0 && (c & 31) == 0 && !superMayHit(T, sup0 + (c >> 5), o, inv, zl, slack)) { c += 31; continue; }
+                    if (COUNT) ctr->boxes++;
                     if (!chunkMayHit(T, (int)nd.z + c, o, inv, zl, slack)) continue;
                     b = start + 32 * c; e = b + 32 < start + count ? b + 32 : start + count;
                 }
@@ -326,7 +328,10 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
                 for (int i = b; i < e; i++) {
                     TriHot tr = loadTri(T, i);
                     float u, v, z;
-                    if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, i, tr.canon, o, d, u, v, z, eps, tr.canon, H.tri, H);
+                    if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) {
+                        if (COUNT) ctr->hits++;
+                        acceptHit(T, i, tr.canon, o, d, u, v, z, eps, tr.canon, H.tri, H);
+                    }
                 }
             }
         }

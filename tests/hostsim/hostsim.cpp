@@ -14,7 +14,7 @@ extern "C" void hostsim_set_refine(int leafMax) { g_refine = leafMax; }
 
 extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris,
                              int materialSize, const kdpt_ray* rays, const float* tMinIn, int n, kdpt_hit* hits,
-                             int mode, unsigned long long* counters /* nodes, leaves, tris or NULL */,
+                             int mode, unsigned long long* counters /* nodes, leaves, tris, boxes, hits (5) or NULL */,
                              float* lastBary /* n*3 or NULL, ref modes */)
 {
     FlatTree F; std::string err;
@@ -42,14 +42,14 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
         X.entryOf = F.entryOf.data();
         X.numNodes = (int)F.xnodes.size(); X.numTris = F.xNumTris;
     }
-    TraceCounters tc = {0, 0, 0};
-    unsigned long long cn = 0, cl = 0, ct = 0;
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    unsigned long long cn = 0, cl = 0, ct = 0, cb = 0, ch = 0;
     for (int i = 0; i < n; i++) {
         V3 o = mk(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]);
         V3 d = mk(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
         float tin = tMinIn ? tMinIn[i] : FLT_MAX;
         Hit H;
-        tc.nodes = tc.leaves = tc.tris = 0;
+        tc.nodes = tc.leaves = tc.tris = tc.boxes = tc.hits = 0;
         switch (mode) {
         case KDPT_FULLSTACK: traceExact<kMaxDepth, true>(X, o, d, tin, 0.00001f, H, &tc); break;
         case KDPT_SHORTSTACK: traceExact<4, true>(X, o, d, tin, 0.0001f, H, &tc); break;
@@ -58,11 +58,11 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
         case KDPT_REF_T2: traceRef<true>(T, o, d, tin, H, lastBary ? lastBary + 3 * i : nullptr); break;
         default: return -2;
         }
-        cn += tc.nodes; cl += tc.leaves; ct += tc.tris;
+        cn += tc.nodes; cl += tc.leaves; ct += tc.tris; cb += tc.boxes; ch += tc.hits;
         hits[i].t = H.t; hits[i].z = H.z; hits[i].u = H.u; hits[i].v = H.v; hits[i].tri = H.tri;
         hits[i].normal[0] = H.nx; hits[i].normal[1] = H.ny; hits[i].normal[2] = H.nz;
     }
-    if (counters) { counters[0] = cn; counters[1] = cl; counters[2] = ct; }
+    if (counters) { counters[0] = cn; counters[1] = cl; counters[2] = ct; counters[3] = cb; counters[4] = ch; }
     return 0;
 }
 

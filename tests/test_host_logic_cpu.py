@@ -19,7 +19,7 @@ def _sim(hostsim, g, mode, tmin=None, nmat=6, rays=None, refine=-1):
     n = len(rays)
     out = np.zeros(n, kdpt.HIT)
     lb = np.zeros((n, 3), 'f4')
-    ctr = np.zeros(3, 'u8')
+    ctr = np.zeros(5, 'u8')
     rc = hostsim.hostsim_trace(P(g['nodes']), len(g['nodes']), P(g['tris']), len(g['tris']), nmat, P(rays),
                                P(tmin) if tmin is not None else None, n, P(out), mode, P(ctr), P(lb))
     assert rc == 0

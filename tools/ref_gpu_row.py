@@ -1,5 +1,6 @@
-"""The "reference-on-B200" row: the reference's OWN CUDA kernels (src/pathtrace.cu, recompiled for sm_100 into
-oracle/_ref/libkdref.so, default fmad as in its own build) rendering the same scene on this GPU, timed beside libkdpt.so in
+"""The "reference-on-B200" row: the reference's OWN CUDA kernels (src/pathtrace.cu recompiled for sm_100, default
+fmad as in its own build; oracle/_ref/libkdref_gpu.so = the temp copy with one guard slot in front of `nodeIDs[]`, see
+oracle/Makefile — the unmodified build, --lib libkdref.so, faults on the B200) rendering the same scene on this GPU, timed beside libkdpt.so in
 the reference-compatible mode, and the two images compared. TEST / MEASUREMENT INFRASTRUCTURE: needs oracle/_ref (built
 where /root/reference exists; the .so travels to the GPU box).
 
@@ -15,15 +16,26 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scene", default="cornell8.txt"); ap.add_argument("--obj", default="stanford_bunny.obj")
 ap.add_argument("--res", default="800x800"); ap.add_argument("--spp", type=int, default=32)
 ap.add_argument("--t1", action="store_true", help="SHORTSTACK off (traverseKDbare) instead of the reference's default short-stack")
+ap.add_argument("--lib", default="libkdref_gpu.so", help="libkdref_gpu.so (nodeIDs guard slot) or libkdref.so (unmodified)")
 ap.add_argument("--check", action="store_true", help="exit non-zero unless the images agree (RMSE < 2 %% of the mean radiance)")
 args = ap.parse_args()
 W, H = (int(v) for v in args.res.split("x"))
 scenes = os.path.join(ROOT, "tests", "golden", "scenes")
-so = os.path.join(ROOT, "oracle", "_ref", "libkdref.so")
+so = os.path.join(ROOT, "oracle", "_ref", args.lib)
 if not os.path.exists(so):
-    print(json.dumps({"unavailable": "oracle/_ref/libkdref.so not built"})); sys.exit(0 if not args.check else 3)
+    print(json.dumps({"unavailable": "oracle/_ref/%s not built" % args.lib})); sys.exit(0 if not args.check else 3)
 R = ctypes.CDLL(so)
 P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+if not os.path.exists(os.path.join(scenes, args.obj)) and os.path.exists(os.path.join(scenes, args.obj + ".gz")):
+    # the larger reference meshes are kept compressed in the fixture directory: unpack next to the scene files' copies
+    import gzip, shutil, tempfile
+    tmpd = tempfile.mkdtemp(prefix="kdpt_scenes_")
+    for f in os.listdir(scenes):
+        if not f.endswith(".gz"):
+            shutil.copy(os.path.join(scenes, f), tmpd)
+    with gzip.open(os.path.join(scenes, args.obj + ".gz")) as fi, open(os.path.join(tmpd, args.obj), "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    scenes = tmpd
 devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
 rc = R.kdref_load(os.path.join(scenes, args.scene).encode(), os.path.join(scenes, args.obj).encode(), (scenes + "/").encode())
 os.dup2(saved, 1)
@@ -47,13 +59,27 @@ rc = R.kdref_gpu_render(P(camb), 1, 2, 6.0, 0.0, 1, 0.0, 0, 1, 0 if args.t1 else
 t0 = time.perf_counter()
 rc2 = R.kdref_gpu_render(P(camb), 1, N, 6.0, 0.0, 1, 0.0, 0, 1, 0 if args.t1 else 1, 0, P(ref))
 t_ref = time.perf_counter() - t0
+# once more with the reference's TESTINGMODE: it prints the summed CUDA-event time of its intersect kernel per iteration
+# (pathtrace.cu:2565-2574, 2612-2616 — the number all of the reference's published benchmarks are made of)
+import tempfile
+tf = tempfile.TemporaryFile(mode="w+b"); os.dup2(tf.fileno(), 1)
+ref2 = np.zeros((H, W, 3), 'f4')
+rc3 = R.kdref_gpu_render(P(camb), 1, N, 6.0, 0.0, 1, 0.0, 0, 1, 0 if args.t1 else 1, 1, P(ref2))
+ctypes.CDLL(None).fflush(None)
 os.dup2(saved, 1)
-assert rc == 0 and rc2 == 0, "reference GPU render failed"
+tf.seek(0)
+ref_isect_ms = [float(l.split(b"=")[1]) for l in tf.read().splitlines() if b"pathTrace time" in l]
+assert rc == 0 and rc2 == 0 and rc3 == 0, "reference GPU render failed"
 p = kdpt.default_params(mode=mode, sortByMaterial=1)
 with kdpt.Context(sc) as ctx:
     ctx.clear_image(); ctx.render(1, 2, 1, p)                         # warm-up
     ctx.clear_image()
     t0 = time.perf_counter(); st = ctx.render(1, N, 1, p); img = ctx.image(); t_own = time.perf_counter() - t0
+    pt = kdpt.default_params(mode=mode, sortByMaterial=1, testingmode=1)
+    ctx.clear_image(); stt = ctx.render(1, N, 1, pt)
+    # the exact-hit mode of the same traversal family (what a user who does not need the reference's dropped hits runs)
+    px = kdpt.default_params(mode=kdpt.FULLSTACK if args.t1 else kdpt.SHORTSTACK, sortByMaterial=1, testingmode=1)
+    ctx.clear_image(); ctx.render(1, 2, 1, px); ctx.clear_image(); stx = ctx.render(1, N, 1, px)
     # the reference's cadence: one call and one image copy per sample (what the INTEGRATION.md shim does)
     ctx.clear_image()
     t0 = time.perf_counter()
@@ -67,6 +93,17 @@ rmse = float(np.sqrt(((img.astype('f8') - ref) ** 2).mean()))
 close = float((np.abs(img - ref) <= 1e-3 * N + 1e-3 * np.abs(ref)).all(axis=2).mean())
 out = {"scene": args.scene, "obj": args.obj, "resolution": [W, H], "spp": N, "mode": "ref_t1" if args.t1 else "ref_t2",
        "ray_bounces": int(rays),
+       "lib": args.lib,
+       "reference_gpu_testingmode": {"intersect_ms_per_iteration": float(np.mean(ref_isect_ms)) if ref_isect_ms else None,
+                                     "iterations": len(ref_isect_ms),
+                                     "mrays_per_s_intersect_kernel": (rays / N) / (np.mean(ref_isect_ms) * 1e-3) / 1e6 if ref_isect_ms else None,
+                                     "what": "the reference's own TESTINGMODE number: CUDA-event time of pathTraceOneBounceKDbare summed over the bounces of one iteration"},
+       "libkdpt_testingmode_same_mode": {"intersect_ms_per_iteration": stt["intersect_ms"] / N,
+                                         "mrays_per_s_intersect_kernel": stt["ray_bounces"] / (stt["intersect_ms"] * 1e-3) / 1e6,
+                                         "what": "kdpt_params.testingmode: CUDA-event time of bounceKernel (intersect + scatter + shade + gather fused) per iteration"},
+       "libkdpt_testingmode_exact_mode": {"intersect_ms_per_iteration": stx["intersect_ms"] / N,
+                                          "mrays_per_s_intersect_kernel": stx["ray_bounces"] / (stx["intersect_ms"] * 1e-3) / 1e6,
+                                          "mrays_per_s_whole_loop": stx["ray_bounces"] / (stx["total_ms"] * 1e-3) / 1e6},
        "reference_gpu": {"seconds": t_ref, "mrays_per_s": rays / t_ref / 1e6, "spp_per_s": N / t_ref,
                          "what": "pathtraceInit + N x pathtrace() + pathtraceFree of the UNMODIFIED src/pathtrace.cu (sm_100 build) on this GPU"},
        "libkdpt_same_mode": {"seconds": t_own, "mrays_per_s": rays / t_own / 1e6, "spp_per_s": N / t_own, "what": "kdpt_render(1..N) + kdpt_get_image, host wall clock"},
