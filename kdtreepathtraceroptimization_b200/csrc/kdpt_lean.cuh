@@ -1,0 +1,153 @@
+// kdpt_lean.cuh — exact closest hit on the REFINED tree: one ray per lane, lanes refilled as their rays finish.
+//
+// The refined view (kdpt_flatten.cpp:refineLeaves) has small leaves, so there is nothing for a warp to share inside a
+// leaf: every lane walks its own ray — the same near-first traversal, early-exit rule and triangle arithmetic as
+// traceExact / traceExactWarp in kdpt_core.cuh, hence the same hits, bit for bit — and what decides the speed is how
+// many lanes have a ray at any time. A packet-at-a-time kernel idles the lanes of short rays until the longest ray of
+// the packet is done (the soups: 2 to 100 leaves per ray). Here a lane whose ray has finished takes the next ray of
+// the batch at the top of the loop, so a warp stays full until the batch runs dry.
+//
+// Per-ray stack: a pending far child needs only (node, exit distance): its entry distance is the exit distance of
+// whatever was traversed before it (the intervals of a kd traversal tile the ray), and the entries lie along the ray
+// in stack order — so the first popped entry that begins beyond the best hit ends the ray. The first
+// kLeanSmemStack entries per lane live in shared memory ([depth][thread]: conflict-free whatever the depths), deeper
+// ones in local memory. RESTART (the short-stack mode): shared-memory ring only; a push onto a full ring drops the
+// OLDEST (farthest) entry, and a ray that runs out of entries after a drop restarts at the root from where it is.
+#pragma once
+#include "kdpt_core.cuh"
+
+namespace kdpt {
+
+#ifndef KDPT_LEAN_THREADS
+#define KDPT_LEAN_THREADS 128
+#endif
+#ifndef KDPT_LEAN_SMEM_STACK
+#define KDPT_LEAN_SMEM_STACK 12
+#endif
+#ifndef KDPT_LEAN_REFILL_MIN
+#define KDPT_LEAN_REFILL_MIN 1      // idle lanes needed before the warp fetches new rays (while rays are left)
+#endif
+constexpr int kLeanThreads = KDPT_LEAN_THREADS;
+constexpr int kLeanSmemStack = KDPT_LEAN_SMEM_STACK;
+constexpr int kLeanRing = 8;        // RESTART: entries in the ring
+
+struct HitCand { float t, nx, ny, nz; int mtl; };
+// interpolated normal, nudged point and its distance (pathtrace.cu:993-998) of a triangle glm accepted: the rare part of
+// the leaf loop, kept out of line so that the loop itself stays small
+__device__ __noinline__ HitCand nudgedHit(const float4* __restrict__ nrmA, const float4* __restrict__ nrmB, const float2* __restrict__ nrmC,
+                                          int i, float ox, float oy, float oz, float dx, float dy, float dz, float u, float v, float z, float eps)
+{
+    const float4 a = __ldg(nrmA + i), b = __ldg(nrmB + i);
+    const float2 c = __ldg(nrmC + i);
+    const V3 o = mk(ox, oy, oz), d = mk(dx, dy, dz);
+    const V3 n1 = mk(a.x, a.y, a.z), n2 = mk(a.w, b.x, b.y), n3 = mk(b.z, b.w, c.x);
+    V3 hp = o + d * z;
+    const V3 nrm = normalize(((1 - u - v) * n1 + u * n2) + v * n3);
+    hp = hp + nrm * eps;
+    HitCand r;
+    r.t = length(hp - o); r.nx = nrm.x; r.ny = nrm.y; r.nz = nrm.z; r.mtl = __float_as_int(c.y);
+    return r;
+}
+
+// Per-lane traversal state between two steps of the lean loop.
+struct LeanState {
+    V3 o, d, inv;
+    float tmin, tmax, t1, slack, zbound;
+    unsigned cur;
+    int sp, ringBase;
+    bool dropped;
+};
+
+// ray set-up shared by the kernels: false = the ray never enters the tree (H stays the "no hit" record)
+__device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinIn, LeanState& S, Hit& H)
+{
+    initHit(H, tMinIn);
+    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = 0;
+    if (T.numNodes == 0) return false;
+    const float len = length(d);
+    if (!(len > 0.0f) || !(len <= FLT_MAX)) return false;
+    S.slack = kExitSlack / len;
+    S.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float t0, t1;
+    if (!slab(o, S.inv, T.rootLo, T.rootHi, t0, t1)) return false;
+    if (!(t0 > 0.0f)) t0 = 0.0f;
+    S.zbound = tMinIn < FLT_MAX ? tMinIn / len : FLT_MAX;
+    S.tmin = t0; S.tmax = t1; S.t1 = t1;
+    return true;
+}
+
+// One step for a lane that has a ray: descend to the next leaf, test it, pop. Returns false when the ray is finished.
+// sStack = this lane's column of the block's shared stack ([k * kLeanThreads]), lStack = its local overflow.
+template <bool RESTART>
+__device__ __forceinline__ bool leanStep(const Tree& T, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack)
+{
+    const V3 o = S.o, d = S.d, inv = S.inv;
+    unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
+    uint4 nd = __ldg(T.nodes + cur);
+    while ((nd.w & 3u) != kLeafFlag) {
+        const int a = (int)(nd.w & 3u);
+        const float split = __int_as_float((int)nd.x);
+        const float oa = comp(o, a), da = comp(d, a), ia = comp(inv, a);
+        const bool below = oa < split || (oa == split && da <= 0.0f);
+        const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+        const float tp = (split - oa) * ia;
+        if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
+        else if (tp <= tmin) cur = farc;
+        else {
+            const uint2 e = make_uint2(farc, __float_as_uint(tmax));
+            if (RESTART) {
+                if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
+                sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
+            } else {
+                if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
+                else lStack[S.sp - kLeanSmemStack] = e;
+            }
+            S.sp++;
+            cur = nearc; tmax = tp;
+        }
+        nd = __ldg(T.nodes + cur);
+    }
+    const int start = (int)nd.x, count = (int)nd.y;
+    if (count > 0) {
+        const int nch = nd.z != kNoChunks ? (count + 31) >> 5 : 1;
+        const int sup0 = nd.z != kNoChunks ? superFirst(T, nd.z) : -1;
+        for (int c = 0; c < nch; c++) {
+            int b = start, e = start + count;
+            if (nd.z != kNoChunks) {        // a leaf the refinement could not split (>= 128 coincident triangles): chunk boxes
+                const float zl = (H.tri >= 0 ? fminf(H.z, S.zbound) : S.zbound) + S.slack;
+                if (sup0 >= 0 && (c & 31) == 0 && !superMayHit(T, sup0 + (c >> 5), o, inv, zl, S.slack)) { c += 31; continue; }
+                if (!chunkMayHit(T, (int)nd.z + c, o, inv, zl, S.slack)) continue;
+                b = start + 32 * c; e = b + 32 < start + count ? b + 32 : start + count;
+            }
+            for (int i = b; i < e; i++) {
+                const TriHot tr = loadTri(T, i);
+                float u, v, z;
+                if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) {
+                    const int ni = T.entryOf ? __ldg(T.entryOf + tr.canon) : i;
+                    const HitCand hc = nudgedHit(T.nrmA, T.nrmB, T.nrmC, ni, o.x, o.y, o.z, d.x, d.y, d.z, u, v, z, eps);
+                    if (hc.t > 0.0f && (H.t > hc.t || (H.t == hc.t && H.tri >= 0 && tr.canon < H.tri))) {
+                        H.t = hc.t; H.z = z; H.u = u; H.v = v; H.tri = tr.canon; H.nx = hc.nx; H.ny = hc.ny; H.nz = hc.nz; H.mtl = hc.mtl;
+                    }
+                }
+            }
+        }
+    }
+    // next pending subtree: it begins where this leaf's cell ends
+    const float zb = (H.tri >= 0 ? fminf(H.z, S.zbound) : S.zbound) + S.slack;
+    if (S.sp > 0) {
+        if (tmax > zb) return false;            // ... beyond the best hit: so do all the others (they lie farther along the ray)
+        S.sp--;
+        uint2 e;
+        if (RESTART) e = sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads];
+        else e = S.sp < kLeanSmemStack ? sStack[S.sp * kLeanThreads] : lStack[S.sp - kLeanSmemStack];
+        S.cur = e.x; S.tmin = tmax; S.tmax = __uint_as_float(e.y);
+        return true;
+    }
+    if (RESTART && S.dropped && !(tmax >= S.t1 || tmax > zb)) {      // kd-restart: everything up to the exit of this leaf is done
+        S.cur = 0; S.tmin = tmax; S.tmax = S.t1; S.ringBase = 0; S.dropped = false;
+        return true;
+    }
+    return false;
+}
+
+} // namespace kdpt

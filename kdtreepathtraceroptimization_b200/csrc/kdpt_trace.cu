@@ -3,6 +3,7 @@
 // Replaces the per-ray body of pathTraceOneBounceKDbare (src/pathtrace.cu:1651-1681): traverseKDbare (881-1020) and
 // traverseKDbareShortHybrid (1023-1235). Compiled with -fmad=false: see kdpt_core.cuh.
 #include "kdpt_internal.h"
+#include "kdpt_lean.cuh"
 #include <stdlib.h>
 
 namespace kdpt {
@@ -81,6 +82,60 @@ traceKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__
             float4* out = reinterpret_cast<float4*>(hits + i);
             out[0] = make_float4(H.t, H.z, H.u, H.v);
             out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
+        }
+    }
+}
+
+// ---- the refined tree: one ray per lane, lanes refilled as their rays finish (kdpt_lean.cuh) ----------------------------
+#ifndef KDPT_LEAN_MIN_BLOCKS
+#define KDPT_LEAN_MIN_BLOCKS 8
+#endif
+template <bool RESTART>
+__global__ void __launch_bounds__(kLeanThreads, KDPT_LEAN_MIN_BLOCKS)
+traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__ tMinIn, int n, kdpt_hit* __restrict__ hits,
+                unsigned* __restrict__ counter, const unsigned* __restrict__ order, float eps)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    __shared__ uint2 sStackAll[(RESTART ? kLeanRing : kLeanSmemStack) * kLeanThreads];
+    uint2* sStack = sStackAll + threadIdx.x;
+    uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
+    LeanState S; Hit H;
+    bool alive = false, more = true;
+    unsigned ray = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !alive);
+        if (more && __popc(idle) >= KDPT_LEAN_REFILL_MIN) {
+            // idle lanes take the next rays of the batch (binned batches: neighbours in leaf order)
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned)__popc(idle) >= (unsigned)n) more = false;
+            if (!alive) {
+                unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (i < (unsigned)n) {
+                    if (order) i = __ldg(order + i);
+                    const float* r = reinterpret_cast<const float*>(rays + i);
+                    const V3 o = mk(__ldg(r + 0), __ldg(r + 1), __ldg(r + 2)), d = mk(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
+                    const float tin = tMinIn ? __ldg(tMinIn + i) : FLT_MAX;
+                    ray = i;
+                    alive = leanBegin(T, o, d, tin, S, H);
+                    if (!alive) {       // never enters the tree
+                        float4* out = reinterpret_cast<float4*>(hits + i);
+                        out[0] = make_float4(H.t, H.z, H.u, H.v);
+                        out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
+        if (alive) {
+            alive = leanStep<RESTART>(T, S, H, eps, sStack, lStack);
+            if (!alive) {
+                float4* out = reinterpret_cast<float4*>(hits + ray);
+                out[0] = make_float4(H.t, H.z, H.u, H.v);
+                out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
+            }
         }
     }
 }
@@ -198,6 +253,18 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
     int grid = ctx->numSMs * blocksPerSM;
     int need = (n + kTraceThreads - 1) / kTraceThreads;
     if (grid > need) grid = need;
+    // exact modes on a refined tree: the lean kernel (KDPT_LEAN=0 keeps the packet kernel, development switch)
+    static const int envLean = getenv("KDPT_LEAN") ? atoi(getenv("KDPT_LEAN")) : 1;
+    if (exact && envLean && ctx->xtree.entryOf) {
+        static const int envBlocks = getenv("KDPT_LEAN_BLOCKS") ? atoi(getenv("KDPT_LEAN_BLOCKS")) : KDPT_LEAN_MIN_BLOCKS;
+        int lgrid = ctx->numSMs * envBlocks;
+        const int lneed = (n + kLeanThreads - 1) / kLeanThreads;
+        if (lgrid > lneed) lgrid = lneed;
+        if (mode == KDPT_FULLSTACK) traceLeanKernel<false><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.00001f);
+        else traceLeanKernel<true><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.0001f);
+        KDPT_CUDA(cudaGetLastError());
+        return KDPT_OK;
+    }
     switch (mode) {
     case KDPT_FULLSTACK: traceKernel<KDPT_FULLSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_SHORTSTACK: traceKernel<KDPT_SHORTSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
