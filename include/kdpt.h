@@ -216,6 +216,11 @@ int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_
  * intersect stage wrote. path_index == array index, as in the reference. */
 int kdpt_bounce(kdpt_ctx* ctx, int iter, int depth, const kdpt_params* params, kdpt_path_segment* paths, int n,
                 kdpt_intersection* isects, int stages);
+/* the loop's other two stages on a caller-owned HOST array, through the same kernels the render loop launches:
+ * thrust::remove_if(paths, is_zero_bounce) (pathtrace.cu:2591-2597, predicate 103-110): stable, in place, *n_out survivors;
+ * thrust::sort(paths) on materialIdHit (pathtrace.cu:2600-2606, operator< 123-131): stable, in place, keys >= -1 */
+int kdpt_compact_paths(kdpt_ctx* ctx, kdpt_path_segment* paths, int n, int* n_out);
+int kdpt_sort_paths(kdpt_ctx* ctx, kdpt_path_segment* paths, int n);
 int kdpt_clear_image(kdpt_ctx* ctx);
 /* A camera move without rebuilding anything. The reference answers every camera change with pathtraceFree +
  * pathtraceInit (main.cpp:1134-1137): a re-upload of the whole tree, and here a re-flatten as well (1 s for 10 M

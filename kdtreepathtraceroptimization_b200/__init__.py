@@ -123,6 +123,8 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_scene_triangle_sources.restype = ctypes.POINTER(ctypes.c_int)
     lib.kdpt_scene_free.argtypes = [vp]
     lib.kdpt_scene_free.restype = None
+    lib.kdpt_compact_paths.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
+    lib.kdpt_sort_paths.argtypes = [vp, vp, ci]
     lib.kdpt_clear_image.argtypes = [vp]
     lib.kdpt_set_camera.argtypes = [vp, vp]
     lib.kdpt_set_stream.argtypes = [vp, vp]
@@ -383,6 +385,21 @@ class Context:
         _check(self._lib.kdpt_bounce(self._h, int(iteration), int(depth), ctypes.byref(p), _ptr(paths), len(paths),
                                      _ptr(isects), int(stages)), "kdpt_bounce")
         return paths, isects
+
+    def compact_paths(self, paths: np.ndarray) -> np.ndarray:
+        """kdpt_compact_paths: the render loop's stream compaction (stable remove_if remainingBounces == 0) on PathSegment records"""
+        paths = np.ascontiguousarray(paths.copy())
+        assert paths.dtype.itemsize == PATH.itemsize
+        m = ctypes.c_int()
+        _check(self._lib.kdpt_compact_paths(self._h, _ptr(paths), len(paths), ctypes.byref(m)), "kdpt_compact_paths")
+        return paths[:m.value]
+
+    def sort_paths(self, paths: np.ndarray) -> np.ndarray:
+        """kdpt_sort_paths: the render loop's stable radix sort by materialIdHit on PathSegment records"""
+        paths = np.ascontiguousarray(paths.copy())
+        assert paths.dtype.itemsize == PATH.itemsize
+        _check(self._lib.kdpt_sort_paths(self._h, _ptr(paths), len(paths)), "kdpt_sort_paths")
+        return paths
 
     def set_camera(self, camera: np.ndarray):
         """kdpt_set_camera: new camera (CAMERA[1], resolution included), radiance buffer cleared, tree untouched"""

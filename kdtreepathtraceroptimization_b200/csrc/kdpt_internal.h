@@ -52,7 +52,7 @@ struct kdpt_ctx {
     // traversal scratch
     kdpt::DeviceBuffer rays, tmin, hits, counter, binTmp;
     // render loop state
-    kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist, accum;
+    kdpt::DeviceBuffer image, pathsA, pathsB, isects, scanTmp, keysTmp, hist, accum, gqWork, gqHit;
     int pixelCount = 0;
     float* boundImage = nullptr;        // caller-owned radiance buffer (kdpt_bind_image)
     cudaStream_t ownStream = nullptr;   // `stream` may point at a caller's stream (kdpt_set_stream)

@@ -34,7 +34,7 @@ constexpr int kLeanRing = 8;        // RESTART: entries in the ring
 struct HitCand { float t, nx, ny, nz; int mtl; };
 // interpolated normal, nudged point and its distance (pathtrace.cu:993-998) of a triangle glm accepted: the rare part of
 // the leaf loop, kept out of line so that the loop itself stays small
-__device__ __noinline__ HitCand nudgedHit(const float4* __restrict__ nrmA, const float4* __restrict__ nrmB, const float2* __restrict__ nrmC,
+static __device__ __noinline__ HitCand nudgedHit(const float4* __restrict__ nrmA, const float4* __restrict__ nrmB, const float2* __restrict__ nrmC,
                                           int i, float ox, float oy, float oz, float dx, float dy, float dz, float u, float v, float z, float eps)
 {
     const float4 a = __ldg(nrmA + i), b = __ldg(nrmB + i);
@@ -49,12 +49,13 @@ __device__ __noinline__ HitCand nudgedHit(const float4* __restrict__ nrmA, const
     return r;
 }
 
-// Per-lane traversal state between two steps of the lean loop.
+// Per-lane traversal state between two rounds of the lean loop.
 struct LeanState {
     V3 o, d, inv;
     float tmin, tmax, t1, slack, zbound;
     unsigned cur;
     int sp, ringBase;
+    int li, le;         // leaf cursor: li < le = the lane is inside a leaf (next entry li), else at node `cur`
     bool dropped;
 };
 
@@ -62,7 +63,7 @@ struct LeanState {
 __device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinIn, LeanState& S, Hit& H)
 {
     initHit(H, tMinIn);
-    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = 0;
+    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = 0; S.li = 0; S.le = 0;
     if (T.numNodes == 0) return false;
     const float len = length(d);
     if (!(len > 0.0f) || !(len <= FLT_MAX)) return false;
@@ -76,63 +77,11 @@ __device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinI
     return true;
 }
 
-// One step for a lane that has a ray: descend to the next leaf, test it, pop. Returns false when the ray is finished.
-// sStack = this lane's column of the block's shared stack ([k * kLeanThreads]), lStack = its local overflow.
+// the leaf at hand is done: take the next pending subtree — it begins where this leaf's cell ends. false = ray finished.
 template <bool RESTART>
-__device__ __forceinline__ bool leanStep(const Tree& T, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack)
+__device__ __forceinline__ bool leanPop(LeanState& S, const Hit& H, const uint2* sStack, const uint2* lStack)
 {
-    const V3 o = S.o, d = S.d, inv = S.inv;
-    unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
-    uint4 nd = __ldg(T.nodes + cur);
-    while ((nd.w & 3u) != kLeafFlag) {
-        const int a = (int)(nd.w & 3u);
-        const float split = __int_as_float((int)nd.x);
-        const float oa = comp(o, a), da = comp(d, a), ia = comp(inv, a);
-        const bool below = oa < split || (oa == split && da <= 0.0f);
-        const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
-        const float tp = (split - oa) * ia;
-        if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
-        else if (tp <= tmin) cur = farc;
-        else {
-            const uint2 e = make_uint2(farc, __float_as_uint(tmax));
-            if (RESTART) {
-                if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
-                sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
-            } else {
-                if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
-                else lStack[S.sp - kLeanSmemStack] = e;
-            }
-            S.sp++;
-            cur = nearc; tmax = tp;
-        }
-        nd = __ldg(T.nodes + cur);
-    }
-    const int start = (int)nd.x, count = (int)nd.y;
-    if (count > 0) {
-        const int nch = nd.z != kNoChunks ? (count + 31) >> 5 : 1;
-        const int sup0 = nd.z != kNoChunks ? superFirst(T, nd.z) : -1;
-        for (int c = 0; c < nch; c++) {
-            int b = start, e = start + count;
-            if (nd.z != kNoChunks) {        // a leaf the refinement could not split (>= 128 coincident triangles): chunk boxes
-                const float zl = (H.tri >= 0 ? fminf(H.z, S.zbound) : S.zbound) + S.slack;
-                if (sup0 >= 0 && (c & 31) == 0 && !superMayHit(T, sup0 + (c >> 5), o, inv, zl, S.slack)) { c += 31; continue; }
-                if (!chunkMayHit(T, (int)nd.z + c, o, inv, zl, S.slack)) continue;
-                b = start + 32 * c; e = b + 32 < start + count ? b + 32 : start + count;
-            }
-            for (int i = b; i < e; i++) {
-                const TriHot tr = loadTri(T, i);
-                float u, v, z;
-                if (rayTriHit(o, d, tr.v0, tr.e1, tr.e2, u, v, z)) {
-                    const int ni = T.entryOf ? __ldg(T.entryOf + tr.canon) : i;
-                    const HitCand hc = nudgedHit(T.nrmA, T.nrmB, T.nrmC, ni, o.x, o.y, o.z, d.x, d.y, d.z, u, v, z, eps);
-                    if (hc.t > 0.0f && (H.t > hc.t || (H.t == hc.t && H.tri >= 0 && tr.canon < H.tri))) {
-                        H.t = hc.t; H.z = z; H.u = u; H.v = v; H.tri = tr.canon; H.nx = hc.nx; H.ny = hc.ny; H.nz = hc.nz; H.mtl = hc.mtl;
-                    }
-                }
-            }
-        }
-    }
-    // next pending subtree: it begins where this leaf's cell ends
+    const float tmax = S.tmax;
     const float zb = (H.tri >= 0 ? fminf(H.z, S.zbound) : S.zbound) + S.slack;
     if (S.sp > 0) {
         if (tmax > zb) return false;            // ... beyond the best hit: so do all the others (they lie farther along the ray)
@@ -148,6 +97,110 @@ __device__ __forceinline__ bool leanStep(const Tree& T, LeanState& S, Hit& H, fl
         return true;
     }
     return false;
+}
+
+__device__ __forceinline__ void leanTestTri(const Tree& T, const LeanState& S, Hit& H, float eps, int i)
+{
+    const TriHot tr = loadTri(T, i);
+    float u, v, z;
+    if (rayTriHit(S.o, S.d, tr.v0, tr.e1, tr.e2, u, v, z)) {
+        const int ni = T.entryOf ? __ldg(T.entryOf + tr.canon) : i;
+        const HitCand hc = nudgedHit(T.nrmA, T.nrmB, T.nrmC, ni, S.o.x, S.o.y, S.o.z, S.d.x, S.d.y, S.d.z, u, v, z, eps);
+        if (hc.t > 0.0f && (H.t > hc.t || (H.t == hc.t && H.tri >= 0 && tr.canon < H.tri))) {
+            H.t = hc.t; H.z = z; H.u = u; H.v = v; H.tri = tr.canon; H.nx = hc.nx; H.ny = hc.ny; H.nz = hc.nz; H.mtl = hc.mtl;
+        }
+    }
+}
+
+// a leaf the refinement could not split (>= 128 coincident triangles): all of it at once, through its chunk boxes.
+// Rare; kept out of line, with everything passed by value so that the callers' ray state stays in registers.
+struct LeanLeafRefs {
+    const float4 *chunkLo, *chunkHi, *superLo, *superHi, *triA, *triB, *nrmA, *nrmB;
+    const float2 *triC, *nrmC;
+    const int* entryOf;
+};
+static __device__ __noinline__ Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V3 inv, float zbound, float slack, Hit H, float eps,
+                                                   int start, int count, unsigned chunk0)
+{
+    Tree T;
+    T.chunkLo = r.chunkLo; T.chunkHi = r.chunkHi; T.superLo = r.superLo; T.superHi = r.superHi;
+    T.triA = r.triA; T.triB = r.triB; T.triC = r.triC; T.nrmA = r.nrmA; T.nrmB = r.nrmB; T.nrmC = r.nrmC; T.entryOf = r.entryOf;
+    LeanState S;
+    S.o = o; S.d = d; S.inv = inv; S.zbound = zbound; S.slack = slack;
+    const int nch = (count + 31) >> 5;
+    const int sup0 = superFirst(T, chunk0);
+    for (int c = 0; c < nch; c++) {
+        const float zl = (H.tri >= 0 ? fminf(H.z, zbound) : zbound) + slack;
+        if (sup0 >= 0 && (c & 31) == 0 && !superMayHit(T, sup0 + (c >> 5), o, inv, zl, slack)) { c += 31; continue; }
+        if (!chunkMayHit(T, (int)chunk0 + c, o, inv, zl, slack)) continue;
+        const int b = start + 32 * c, e = b + 32 < start + count ? b + 32 : start + count;
+        for (int i = b; i < e; i++) leanTestTri(T, S, H, eps, i);
+    }
+    return H;
+}
+
+#ifndef KDPT_LEAN_NODE_WEIGHT
+#define KDPT_LEAN_NODE_WEIGHT 1     // a round takes the leaf step when leafLanes * NODE_WEIGHT > nodeLanes * LEAF_WEIGHT
+#endif
+#ifndef KDPT_LEAN_LEAF_WEIGHT
+#define KDPT_LEAN_LEAF_WEIGHT 1
+#endif
+
+// One round of the warp (all 32 lanes call it; `alive` = the lane has a ray). Rays differ wildly in how many nodes
+// they cross between leaves and in how many triangles their leaves hold, so a "descend to the next leaf, then test the
+// leaf" step makes every lane wait for the longest descent and the fullest leaf of the warp (measured: 6 of 32 lanes
+// active per instruction). Here a round is ONE unit of work — one node step or one triangle test — and the warp takes
+// the kind more of its lanes are waiting for; the others keep their state and wait for a round of their kind.
+// Returns whether the lane still has a ray.
+template <bool RESTART>
+__device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack)
+{
+    const bool inLeaf = alive && S.li < S.le;
+    const unsigned leafMask = __ballot_sync(0xffffffffu, inLeaf);
+    const unsigned nodeMask = __ballot_sync(0xffffffffu, alive && !inLeaf);
+    if (__popc(leafMask) * KDPT_LEAN_NODE_WEIGHT > __popc(nodeMask) * KDPT_LEAN_LEAF_WEIGHT) {
+        if (inLeaf) {
+            leanTestTri(T, S, H, eps, S.li);
+            if (++S.li == S.le) alive = leanPop<RESTART>(S, H, sStack, lStack);
+        }
+        return alive;
+    }
+    if (alive && !inLeaf) {
+        const uint4 nd = __ldg(T.nodes + S.cur);
+        if ((nd.w & 3u) != kLeafFlag) {
+            const int a = (int)(nd.w & 3u);
+            const float split = __int_as_float((int)nd.x);
+            const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+            const bool below = oa < split || (oa == split && da <= 0.0f);
+            const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+            const float tp = (split - oa) * ia;
+            if (da == 0.0f || tp <= 0.0f || tp >= S.tmax) S.cur = nearc;
+            else if (tp <= S.tmin) S.cur = farc;
+            else {
+                const uint2 e = make_uint2(farc, __float_as_uint(S.tmax));
+                if (RESTART) {
+                    if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
+                    sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
+                } else {
+                    if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
+                    else lStack[S.sp - kLeanSmemStack] = e;
+                }
+                S.sp++;
+                S.cur = nearc; S.tmax = tp;
+            }
+        } else {
+            const int start = (int)nd.x, count = (int)nd.y;
+            if (count > 0 && nd.z == kNoChunks) { S.li = start; S.le = start + count; }
+            else {
+                if (count > 0) {
+                    const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
+                    H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
+                }
+                alive = leanPop<RESTART>(S, H, sStack, lStack);
+            }
+        }
+    }
+    return alive;
 }
 
 } // namespace kdpt

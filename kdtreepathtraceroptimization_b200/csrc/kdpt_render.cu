@@ -16,6 +16,7 @@
 //    (RNG seeded by utilhash(iter) only, pathtrace.cu:334), is computed once per iteration on the host.
 #include "kdpt_internal.h"
 #include "kdpt_render.cuh"
+#include "kdpt_lean.cuh"
 #include <string.h>
 
 namespace kdpt {
@@ -49,11 +50,14 @@ struct IterConst {
 constexpr int kMaxBatch = KDPT_MAX_BATCH;   // iterations (samples) processed together by every launch
 constexpr int kSegShift = 26;               // the lane queue packs (segment, path index) in one word: <= 64 segments, < 2^26 paths each
 static_assert(kMaxBatch <= 64, "the lane queue packs the segment in 6 bits");
+constexpr int kWavefrontMinTris = 0;         // refined leaf entries from which the bounce runs in its wavefront form
 constexpr int kTicketPackets = 1;       // 32-path packets a warp takes per ticket (amortises the atomic + segment lookup)
 
 struct LoopState {
     int np[kMaxBatch][kMaxBounces + 2];      // live paths of each batched iteration at the start of each bounce
     unsigned ticket[2 * (kMaxBounces + 1)];  // packet counters: [b] bounce kernel, [9+b] compaction
+    unsigned gqCount[kMaxBounces];           // wavefront form: rays queued for the traversal kernel at each bounce ...
+    unsigned gqTicket[kMaxBounces];          // ... and how many of them the traversal kernel has handed to its lanes
     unsigned long long bounceRays[kMaxBounces];
     unsigned long long travRays[kMaxBounces];   // of those, rays that entered the KD tree's root box
     // entering fraction per bounce depth of the most recent batch (< 0: not measured yet) and the counter values it
@@ -91,6 +95,13 @@ __device__ __forceinline__ int findSegment(const int* pk, int B, int t)
     while (s + 1 < B && t >= pk[s + 1]) s++;
     return s;
 }
+
+// Wavefront form of a bounce (exact modes on a refined tree): the rays that enter the tree are not traversed inside the
+// bounce kernel but appended to a queue in global memory — word-major, one column per ray: the kWorkWords words of its
+// PathWork record — which the lean traversal kernel (kdpt_lean.cuh: one ray per lane, lanes refilled as rays finish)
+// drains into kHitWords words per ray; a third kernel then runs phase C for the queued paths.
+constexpr int kHitWords = 7;        // t, z, tri, nx, ny, nz, mtl
+struct RayQueue { float* work; float* hit; unsigned cap; };
 
 struct SceneView {
     const kdpt_geom* geoms; int numGeoms;
@@ -179,7 +190,10 @@ generateRaysKernel(kdpt_camera cam, IterConsts ics, Batch bt, int traceDepth, fl
 {
     const int n = bt.npix;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0) for (int k = 0; k < 2 * (kMaxBounces + 1); k++) st->ticket[k] = 0;
+    if (g == 0) {
+        for (int k = 0; k < 2 * (kMaxBounces + 1); k++) st->ticket[k] = 0;
+        for (int k = 0; k < kMaxBounces; k++) { st->gqCount[k] = 0; st->gqTicket[k] = 0; }
+    }
     if (g < bt.B) st->np[g][0] = n;
     if (g >= bt.B * n) return;
     const int seg = g / n, index = g - seg * n;
@@ -197,6 +211,7 @@ __global__ void beginBatchKernel(LoopState* st, int B, int npix)
 {
     const int g = threadIdx.x;
     if (g < 2 * (kMaxBounces + 1)) st->ticket[g] = 0;
+    if (g < kMaxBounces) { st->gqCount[g] = 0; st->gqTicket[g] = 0; }
     if (g < B) st->np[g][0] = npix;
 }
 
@@ -302,12 +317,12 @@ __device__ __forceinline__ bool finishPath(PathWork& w, const Hit& H, bool doIse
 //    third or more of the lanes enter the tree anyway (measured: the queue's bookkeeping and the loss of coherence then
 //    cost more than the idle lanes). The kernel picks per launch from the entering fraction it measured at this bounce
 //    depth in the previous batch (LoopState::enterFrac), see bounceKernel.
-template <int MODE, bool GEN, bool QUEUE>
+template <int MODE, bool GEN, bool QUEUE, bool GQ = false>
 __device__ __forceinline__ void
 bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, const BounceArgs& A, const Batch& bt,
            float* __restrict__ accum, int* __restrict__ packetCount, unsigned* __restrict__ packetAlive,
            kdpt_intersection* __restrict__ isectOut, const GenArgs& gen,
-           const kdpt_geom* sGeoms, const float4* sBounds, const int* pk, float* sDefRaw, int ng)
+           const kdpt_geom* sGeoms, const float4* sBounds, const int* pk, float* sDefRaw, int ng, RayQueue gq = RayQueue{nullptr, nullptr, 0})
 {
     constexpr int kSlots = QUEUE ? 64 : 32;
     constexpr int kWords = QUEUE ? kWorkWords : kParkWords;
@@ -331,7 +346,7 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
         w.seg = 0; w.i = 0; w.packet = 0;
         Hit H;
         bool finishNow = false, doIsect = false;
-        const bool drain = QUEUE && (defCount >= 32 || (flushWanted && defCount > 0));
+        const bool drain = QUEUE && !GQ && (defCount >= 32 || (flushWanted && defCount > 0));
         bool alive = false, live = false;
         unsigned defMask = 0;
         if (drain) {
@@ -434,7 +449,26 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
             }
             defMask = __ballot_sync(FULL, needTrav);
             initHit(H, w.tMin);
-            if (QUEUE) {
+            if (GQ) {
+                // wavefront form: lanes whose ray enters the tree append their record to the global queue, the others finish now
+                unsigned qb = 0;
+                if (defMask && lane == 0) qb = atomicAdd(&st->gqCount[A.depth], (unsigned)__popc(defMask));
+                qb = __shfl_sync(FULL, qb, 0);
+                if (needTrav) {
+                    float* q = gq.work + (qb + (unsigned)__popc(defMask & ((1u << lane) - 1u)));
+                    const size_t cs = gq.cap;
+                    q[0] = w.r.o.x; q[cs] = w.r.o.y; q[2 * cs] = w.r.o.z;
+                    q[3 * cs] = w.r.d.x; q[4 * cs] = w.r.d.y; q[5 * cs] = w.r.d.z; q[6 * cs] = w.tMin;
+                    q[7 * cs] = w.r.inside ? 1.0f : 0.0f; q[8 * cs] = w.r.sdepth;
+                    q[9 * cs] = w.cp.x; q[10 * cs] = w.cp.y; q[11 * cs] = w.cp.z; q[12 * cs] = w.cp.w;
+                    q[13 * cs] = __int_as_float(w.bm.x); q[14 * cs] = __int_as_float(w.bm.y);
+                    q[15 * cs] = __int_as_float(w.hitGeom);
+                    q[16 * cs] = w.ipoint.x; q[17 * cs] = w.ipoint.y; q[18 * cs] = w.ipoint.z;
+                    q[19 * cs] = w.normal.x; q[20 * cs] = w.normal.y; q[21 * cs] = w.normal.z;
+                    q[22 * cs] = __int_as_float((int)(((unsigned)w.seg << kSegShift) | (unsigned)w.i));
+                }
+                finishNow = live && !needTrav;
+            } else if (QUEUE) {
                 // lanes whose ray enters the tree go to the queue (fewer than 32 are waiting there), the others finish now
                 if (needTrav) {
                     const int e = (qHead + defCount + __popc(defMask & ((1u << lane) - 1u))) & (kSlots - 1);
@@ -542,6 +576,105 @@ bounceKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch 
     }
     if (!GEN && queue) bounceBody<MODE, false, true>(T, S, P, st, A, bt, accum, packetCount, packetAlive, isectOut, gen, sGeoms, sBounds, pk, sDef, ng);
     else bounceBody<MODE, GEN, false>(T, S, P, st, A, bt, accum, packetCount, packetAlive, isectOut, gen, sGeoms, sBounds, pk, sDef, ng);
+}
+
+// ---- wavefront form: front kernel (phase A, phase C of the paths that do not enter the tree), traversal, finish ------
+template <int MODE, bool GEN>
+__global__ void __launch_bounds__(kThreads, 5)
+frontKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch bt, float* __restrict__ accum,
+            int* __restrict__ packetCount, unsigned* __restrict__ packetAlive, const GenArgs gen, RayQueue gq)
+{
+    __shared__ kdpt_geom sGeoms[kMaxSmemGeoms];
+    __shared__ float4 sBounds[2 * kMaxSmemGeoms];
+    __shared__ int pk[kMaxBatch + 1];
+    const int ng = S.numGeoms < kMaxSmemGeoms ? S.numGeoms : kMaxSmemGeoms;
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(S.geoms);
+        unsigned* dst = reinterpret_cast<unsigned*>(sGeoms);
+        for (int k = threadIdx.x; k < ng * (int)(sizeof(kdpt_geom) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
+        for (int k = threadIdx.x; k < 2 * ng; k += blockDim.x) sBounds[k] = __ldg(S.geomBounds + k);
+    }
+    buildPacketPrefix(pk, st, bt.B, A.depth, kTicketPackets);
+    bounceBody<MODE, GEN, true, true>(T, S, P, st, A, bt, accum, packetCount, packetAlive, nullptr, gen, sGeoms, sBounds, pk, nullptr, ng, gq);
+}
+
+#ifndef KDPT_LEAN_MIN_BLOCKS
+#define KDPT_LEAN_MIN_BLOCKS 8
+#endif
+// the queued rays through the refined tree: kdpt_lean.cuh, rays and results in the queue's columns
+template <bool RESTART>
+__global__ void __launch_bounds__(kLeanThreads, KDPT_LEAN_MIN_BLOCKS)
+traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    __shared__ uint2 sStackAll[(RESTART ? kLeanRing : kLeanSmemStack) * kLeanThreads];
+    uint2* sStack = sStackAll + threadIdx.x;
+    uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
+    const unsigned n = st->gqCount[depth];
+    const size_t cs = gq.cap;
+    LeanState S; Hit H;
+    bool alive = false, more = n > 0;
+    unsigned slot = 0;
+    auto store = [&](unsigned i) {
+        float* h = gq.hit + i;
+        h[0] = H.t; h[cs] = H.z; h[2 * cs] = __int_as_float(H.tri); h[3 * cs] = H.nx; h[4 * cs] = H.ny; h[5 * cs] = H.nz;
+        h[6 * cs] = __int_as_float(H.mtl);
+    };
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !alive);
+        if (more && __popc(idle) >= KDPT_LEAN_REFILL_MIN) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&st->gqTicket[depth], (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned)__popc(idle) >= n) more = false;
+            if (!alive) {
+                const unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    const float* q = gq.work + i;
+                    const V3 o = mk(__ldg(q), __ldg(q + cs), __ldg(q + 2 * cs)), d = mk(__ldg(q + 3 * cs), __ldg(q + 4 * cs), __ldg(q + 5 * cs));
+                    slot = i;
+                    alive = leanBegin(T, o, d, __ldg(q + 6 * cs), S, H);
+                    if (!alive) store(i);
+                }
+            }
+        }
+        if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
+        const bool was = alive;
+        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack);
+        if (was && !alive) store(slot);
+    }
+}
+
+// phase C of the queued paths
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 5)
+finishQueueKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch bt, float* __restrict__ accum,
+                  int* __restrict__ packetCount, unsigned* __restrict__ packetAlive, RayQueue gq)
+{
+    const unsigned n = st->gqCount[A.depth];
+    const size_t cs = gq.cap;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const float* q = gq.work + e;
+        const float* h = gq.hit + e;
+        PathWork w;
+        w.r.o = mk(q[0], q[cs], q[2 * cs]); w.r.d = mk(q[3 * cs], q[4 * cs], q[5 * cs]); w.tMin = q[6 * cs];
+        w.r.inside = q[7 * cs] != 0.0f; w.r.sdepth = q[8 * cs];
+        w.cp = make_float4(q[9 * cs], q[10 * cs], q[11 * cs], q[12 * cs]);
+        w.bm = make_int2(__float_as_int(q[13 * cs]), __float_as_int(q[14 * cs]));
+        w.hitGeom = __float_as_int(q[15 * cs]);
+        w.ipoint = mk(q[16 * cs], q[17 * cs], q[18 * cs]); w.normal = mk(q[19 * cs], q[20 * cs], q[21 * cs]);
+        const int segi = __float_as_int(q[22 * cs]);
+        w.seg = (int)((unsigned)segi >> kSegShift); w.i = segi & ((1 << kSegShift) - 1); w.packet = w.i >> 5;
+        Hit H;
+        H.t = h[0]; H.z = h[cs]; H.u = 0.f; H.v = 0.f; H.tri = __float_as_int(h[2 * cs]); H.nx = h[3 * cs]; H.ny = h[4 * cs]; H.nz = h[5 * cs];
+        H.mtl = __float_as_int(h[6 * cs]); H.anyMtl = H.mtl;
+        const bool alive = finishPath<MODE>(w, H, true, T, S, P, A, bt, accum, packetAlive, nullptr);
+        if (alive) {        // the packet's entry was stored by the front kernel; a queued survivor adds itself
+            if (packetCount) atomicAdd(&packetCount[w.seg * bt.capPackets + w.packet], 1);
+            if (packetAlive) atomicOr(&packetAlive[w.seg * bt.capPackets + w.packet], 1u << (w.i & 31));
+        }
+    }
 }
 
 // ---- stream compaction (replaces thrust::remove_if, pathtrace.cu:2591-2597) ---------------------------------------
@@ -765,7 +898,7 @@ peerGatherKernel(PeerImages pi, int self, size_t per, size_t total)
 __global__ void packPathsKernel(const kdpt_path_segment* __restrict__ in, int n, PathSoA P, LoopState* st, int depth)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { st->np[0][depth] = n; st->ticket[depth] = 0; }
+    if (i == 0) { st->np[0][depth] = n; st->ticket[depth] = 0; st->gqCount[depth] = 0; st->gqTicket[depth] = 0; }
     if (i >= n) return;
     kdpt_path_segment s = in[i];
     P.od[i] = make_float4(s.origin[0], s.origin[1], s.origin[2], s.sdepth);
@@ -786,6 +919,20 @@ __global__ void unpackPathsKernel(PathSoA P, int n, kdpt_path_segment* __restric
     out[i] = s;
 }
 
+// stage-level compaction entry point: packet alive masks / counts from remainingBounces (inside the render loop the
+// bounce kernel leaves them behind itself)
+__global__ void __launch_bounds__(kThreads)
+aliveMaskKernel(PathSoA P, int n, int* __restrict__ packetCount, unsigned* __restrict__ packetAlive)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, numWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int packet = warpId; packet * 32 < n; packet += numWarps) {
+        const int i = packet * 32 + (int)lane;
+        const unsigned mask = __ballot_sync(0xffffffffu, i < n && P.bm[i].x != 0);     // is_zero_bounce, pathtrace.cu:103-110
+        if (lane == 0) { packetCount[packet] = __popc(mask); packetAlive[packet] = mask; }
+    }
+}
+
 // ---- host driver --------------------------------------------------------------------------------------------------
 struct RenderBuffers {
     PathSoA A, B;
@@ -795,10 +942,22 @@ struct RenderBuffers {
     float* image;
     float* accum;
     int cap, capPackets;
+    RayQueue gq;        // wavefront form only (work == nullptr otherwise)
 };
 
 // n = path slots per iteration, batch = iterations per launch
-static int ensureRenderBuffers(kdpt_ctx* ctx, int n, int batch, RenderBuffers& rb, bool needAccum)
+// The wavefront form pays for rays that enter a refined tree with enough in it that traversal dominates the bounce.
+// KDPT_WAVEFRONT=0/1 forces it off/on in development.
+static bool useWavefront(const kdpt_ctx* ctx, int mode)
+{
+    if (mode != KDPT_FULLSTACK && mode != KDPT_SHORTSTACK) return false;
+    if (!ctx->xtree.entryOf) return false;
+    static const int env = getenv("KDPT_WAVEFRONT") ? atoi(getenv("KDPT_WAVEFRONT")) : -1;
+    if (env >= 0) return env != 0;
+    return ctx->xtree.numTris >= kWavefrontMinTris;
+}
+
+static int ensureRenderBuffers(kdpt_ctx* ctx, int n, int batch, RenderBuffers& rb, bool needAccum, bool wavefront = false)
 {
     int rc;
     const size_t per = sizeof(float4) * 3 + sizeof(int2);
@@ -826,6 +985,13 @@ static int ensureRenderBuffers(kdpt_ctx* ctx, int n, int batch, RenderBuffers& r
     if ((rc = ctx->hist.ensure(sizeof(unsigned) * 256 * (size_t)rb.maxTiles * batch))) return rc;
     rb.hist = ctx->hist.as<unsigned>();
     rb.image = ctx->boundImage ? ctx->boundImage : ctx->image.as<float>();
+    rb.gq = RayQueue{nullptr, nullptr, 0};
+    if (wavefront) {
+        if ((rc = ctx->gqWork.ensure(sizeof(float) * kWorkWords * slots)) || (rc = ctx->gqHit.ensure(sizeof(float) * kHitWords * slots))) return rc;
+        rb.gq.work = ctx->gqWork.as<float>(); rb.gq.hit = ctx->gqHit.as<float>();
+        rb.gq.cap = (unsigned)(ctx->gqHit.bytes / (sizeof(float) * kHitWords) < ctx->gqWork.bytes / (sizeof(float) * kWorkWords)
+                               ? ctx->gqHit.bytes / (sizeof(float) * kHitWords) : ctx->gqWork.bytes / (sizeof(float) * kWorkWords));
+    }
     rb.accum = nullptr;
     if (needAccum) {
         if ((rc = ctx->accum.ensure(sizeof(float) * 3 * (size_t)ctx->pixelCount * batch))) return rc;
@@ -870,6 +1036,25 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
     static const int envQueue = getenv("KDPT_QUEUE") ? atoi(getenv("KDPT_QUEUE")) : -1;
     A.queuePolicy = envQueue >= 0 ? envQueue : (p.laneQueue == 1 ? 0 : p.laneQueue == 2 ? 1 : 2);
     const Tree& TV = (p.mode == KDPT_FULLSTACK || p.mode == KDPT_SHORTSTACK) ? ctx->xtree : ctx->tree;
+    if (rb.gq.work && !dIsects) {
+        // wavefront form: front (phase A + the paths that miss the tree) -> lean traversal of the queued rays -> finish
+        static const int envBlocks = getenv("KDPT_LEAN_BLOCKS") ? atoi(getenv("KDPT_LEAN_BLOCKS")) : KDPT_LEAN_MIN_BLOCKS;
+        const int lgrid = ctx->numSMs * envBlocks;
+        if (p.mode == KDPT_FULLSTACK) {
+            if (gen) frontKernel<KDPT_FULLSTACK, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, *gen, rb.gq);
+            else frontKernel<KDPT_FULLSTACK, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, noGen, rb.gq);
+            traceQueueKernel<false><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps);
+            finishQueueKernel<KDPT_FULLSTACK><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, rb.gq);
+        } else {
+            if (gen) frontKernel<KDPT_SHORTSTACK, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, *gen, rb.gq);
+            else frontKernel<KDPT_SHORTSTACK, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, noGen, rb.gq);
+            traceQueueKernel<true><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps);
+            finishQueueKernel<KDPT_SHORTSTACK><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, rb.gq);
+        }
+        launches += 3;
+        KDPT_CUDA(cudaGetLastError());
+        return KDPT_OK;
+    }
 #define KDPT_LAUNCH_BOUNCE(M)                                                                                                   \
     if (gen) bounceKernel<M, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, *gen);   \
     else bounceKernel<M, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, noGen)
@@ -1051,12 +1236,12 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
     const kdpt_params& p = *params;
     const int n = ctx->pixelCount;
     if (n >= (1 << kSegShift)) { setError("kdpt_render: more than 2^26 pixels"); return KDPT_ERR_ARG; }
-    // iterations per launch: bounded by kMaxBatch and by 8 GB of path state (of 180 GB)
+    // iterations per launch: bounded by kMaxBatch and by 16 GB of path state + ray queue (of 180 GB)
     int maxBatch = kMaxBatch;
-    while (maxBatch > 1 && (size_t)maxBatch * n * 128 > ((size_t)8 << 30)) maxBatch >>= 1;
+    while (maxBatch > 1 && (size_t)maxBatch * n * 256 > ((size_t)16 << 30)) maxBatch >>= 1;
     if (iter_count < maxBatch) maxBatch = iter_count > 0 ? iter_count : 1;
     RenderBuffers rb;
-    if ((rc = ensureRenderBuffers(ctx, n, maxBatch, rb, true))) return rc;
+    if ((rc = ensureRenderBuffers(ctx, n, maxBatch, rb, true, useWavefront(ctx, p.mode)))) return rc;
     cudaStream_t s = ctx->stream;
     uint64_t launches = 0;
     unsigned long long before[kMaxBounces], after[kMaxBounces];
@@ -1170,6 +1355,76 @@ int kdpt_generate_rays(kdpt_ctx* ctx, int iter, const kdpt_params* params, kdpt_
     KDPT_CUDA(cudaGetLastError());
     KDPT_CUDA(cudaMemcpyAsync(out, ctx->isects.p, sizeof(kdpt_path_segment) * (size_t)n, cudaMemcpyDeviceToHost, s));
     KDPT_CUDA(cudaStreamSynchronize(s));
+    return KDPT_OK;
+}
+
+// thrust::remove_if(paths, is_zero_bounce) (pathtrace.cu:2591-2597) / thrust::sort by materialIdHit (2600-2606) on a
+// caller-owned HOST array, through the render loop's own kernels
+int kdpt_compact_paths(kdpt_ctx* ctx, kdpt_path_segment* paths, int n, int* n_out)
+{
+    if (!ctx || n < 0 || (n > 0 && !paths) || !n_out) { setError("kdpt_compact_paths: bad argument"); return KDPT_ERR_ARG; }
+    if (n >= (1 << kSegShift)) { setError("kdpt_compact_paths: more than 2^26 paths"); return KDPT_ERR_ARG; }
+    *n_out = 0;
+    if (n == 0) return KDPT_OK;
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    RenderBuffers rb;
+    if ((rc = ensureRenderBuffers(ctx, n, 1, rb, false))) return rc;
+    Batch bt; bt.B = 1; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = 1; bt.iterStride = 1; bt.npix = n;
+    const size_t pb = sizeof(kdpt_path_segment) * (size_t)n;
+    if ((rc = ctx->isects.ensure(pb))) return rc;
+    kdpt_path_segment* dPaths = ctx->isects.as<kdpt_path_segment>();
+    cudaStream_t s = ctx->stream;
+    const int grid = ctx->numSMs * 8;
+    KDPT_CUDA(cudaMemcpyAsync(dPaths, paths, pb, cudaMemcpyHostToDevice, s));
+    packPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(dPaths, n, rb.A, rb.st, 0);
+    aliveMaskKernel<<<grid, kThreads, 0, s>>>(rb.A, n, rb.packetCount, rb.packetAlive);
+    scanPacketsKernel<<<1, 1024, 0, s>>>(rb.packetCount, rb.st, 0, 1, rb.capPackets);
+    compactScatterKernel<<<grid, kThreads, 0, s>>>(rb.A, rb.B, rb.packetCount, rb.packetAlive, rb.st, 0, bt);
+    int m = 0;
+    KDPT_CUDA(cudaMemcpyAsync(&m, &rb.st->np[0][1], sizeof(int), cudaMemcpyDeviceToHost, s));
+    KDPT_CUDA(cudaStreamSynchronize(s));
+    if (m > 0) {
+        unpackPathsKernel<<<(m + 255) / 256, 256, 0, s>>>(rb.B, m, dPaths);
+        KDPT_CUDA(cudaMemcpyAsync(paths, dPaths, sizeof(kdpt_path_segment) * (size_t)m, cudaMemcpyDeviceToHost, s));
+    }
+    KDPT_CUDA(cudaGetLastError());
+    KDPT_CUDA(cudaStreamSynchronize(s));
+    ctx->launches += 5;
+    *n_out = m;
+    return KDPT_OK;
+}
+
+int kdpt_sort_paths(kdpt_ctx* ctx, kdpt_path_segment* paths, int n)
+{
+    if (!ctx || n < 0 || (n > 0 && !paths)) { setError("kdpt_sort_paths: bad argument"); return KDPT_ERR_ARG; }
+    if (n >= (1 << kSegShift)) { setError("kdpt_sort_paths: more than 2^26 paths"); return KDPT_ERR_ARG; }
+    if (n == 0) return KDPT_OK;
+    KDPT_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    RenderBuffers rb;
+    if ((rc = ensureRenderBuffers(ctx, n, 1, rb, false))) return rc;
+    Batch bt; bt.B = 1; bt.cap = rb.cap; bt.capPackets = rb.capPackets; bt.iterBase = 1; bt.iterStride = 1; bt.npix = n;
+    const size_t pb = sizeof(kdpt_path_segment) * (size_t)n;
+    if ((rc = ctx->isects.ensure(pb))) return rc;
+    kdpt_path_segment* dPaths = ctx->isects.as<kdpt_path_segment>();
+    cudaStream_t s = ctx->stream;
+    const int grid = ctx->numSMs * 8;
+    KDPT_CUDA(cudaMemcpyAsync(dPaths, paths, pb, cudaMemcpyHostToDevice, s));
+    packPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(dPaths, n, rb.A, rb.st, 0);
+    // all four key bytes: the caller's materialIdHit values are arbitrary ints here (the render loop knows the material count)
+    PathSoA cur = rb.A, other = rb.B;
+    for (int pass = 0; pass < 4; pass++) {
+        sortHistKernel<<<grid, kSortTile, 0, s>>>(cur, rb.st, 0, 8 * pass, rb.hist, rb.maxTiles, bt);
+        sortScanKernel<<<1, 1024, 0, s>>>(rb.st, 0, rb.hist, rb.maxTiles);
+        sortScatterKernel<<<grid, kSortTile, 0, s>>>(cur, other, rb.st, 0, 8 * pass, rb.hist, rb.maxTiles, bt);
+        PathSoA t = cur; cur = other; other = t;
+    }
+    unpackPathsKernel<<<(n + 255) / 256, 256, 0, s>>>(cur, n, dPaths);
+    KDPT_CUDA(cudaGetLastError());
+    KDPT_CUDA(cudaMemcpyAsync(paths, dPaths, pb, cudaMemcpyDeviceToHost, s));
+    KDPT_CUDA(cudaStreamSynchronize(s));
+    ctx->launches += 14;
     return KDPT_OK;
 }
 

@@ -129,13 +129,12 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
             }
         }
         if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
-        if (alive) {
-            alive = leanStep<RESTART>(T, S, H, eps, sStack, lStack);
-            if (!alive) {
-                float4* out = reinterpret_cast<float4*>(hits + ray);
-                out[0] = make_float4(H.t, H.z, H.u, H.v);
-                out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
-            }
+        const bool was = alive;
+        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack);
+        if (was && !alive) {
+            float4* out = reinterpret_cast<float4*>(hits + ray);
+            out[0] = make_float4(H.t, H.z, H.u, H.v);
+            out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
         }
     }
 }

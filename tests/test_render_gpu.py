@@ -328,3 +328,34 @@ def test_render_edge_cases_match_oracle(oracle, variant):
     assert (np.abs(g - o).max(2) < 1e-3).mean() > 0.99
     if variant != "no_geoms":
         assert o.sum() > 0
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4097, 100003, 640000])
+def test_compaction_and_sort_are_bit_exact(n):
+    """C1 / C2 are index work: the render loop's own compaction kernels (warp-ballot counts -> scan -> stable scatter)
+    and its radix sort, run on caller-owned PathSegment records through kdpt_compact_paths / kdpt_sort_paths, must
+    reproduce thrust::remove_if(is_zero_bounce) and a stable sort on materialIdHit byte for byte — every field of
+    every record in the same order (ragged tails, all-dead / all-alive packets, keys wider than one digit)."""
+    rng = np.random.default_rng(n)
+    sc = _scene("cornell_sphere_low_1.npz", 64, 64)
+    with kdpt.Context(sc) as ctx:
+        for variant in range(3):
+            p = np.zeros(n, kdpt.PATH)
+            p['origin'] = rng.normal(size=(n, 3)); p['direction'] = rng.normal(size=(n, 3)); p['color'] = rng.random((n, 3))
+            p['sdepth'] = rng.random(n); p['isinside'] = rng.integers(0, 2, n)
+            p['pixelIndex'] = rng.permutation(n)
+            if variant == 0:
+                p['remainingBounces'] = rng.integers(0, 3, n)                       # a third of the paths are finished
+                p['materialIdHit'] = rng.integers(-1, 12, n)
+            elif variant == 1:
+                p['remainingBounces'] = (rng.random(n) < 0.03) * rng.integers(1, 8, n)   # almost everything finished, whole packets empty
+                p['materialIdHit'] = rng.integers(-1, 70000, n)                     # keys that need three radix digits
+            else:
+                p['remainingBounces'] = 1 + rng.integers(0, 8, n)                   # nothing finished
+                p['materialIdHit'] = 5
+            got = ctx.compact_paths(p)
+            exp = p[p['remainingBounces'] != 0]
+            assert len(got) == len(exp) and got.tobytes() == exp.tobytes(), (n, variant)
+            got = ctx.sort_paths(p)
+            exp = p[np.argsort(p['materialIdHit'], kind='stable')]
+            assert got.tobytes() == exp.tobytes(), (n, variant)
