@@ -180,9 +180,9 @@ int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out);
  * or when a split keeps all triangles on one side: leaves of hundreds to tens of thousands of triangles). Results do not
  * depend on these options; the reference-compatible modes always walk the tree as given. NULL = defaults. */
 typedef struct {
-    int refineLeafMax;          /* < 0: default (4); 0: no refinement (exact modes walk the reference tree, fat leaves are
+    int refineLeafMax;          /* < 0: default (8); 0: no refinement (exact modes walk the reference tree, fat leaves are
                                    tested warp-cooperatively through chunk boxes); > 0: leaf size at which splitting stops */
-    float refineTraversalCost;  /* <= 0: default (1.0); cost of one node step relative to one triangle test in the builder's
+    float refineTraversalCost;  /* <= 0: default (2.0); cost of one node step relative to one triangle test in the builder's
                                    surface-area heuristic */
     int reserved[6];
 } kdpt_build_opts;

@@ -181,7 +181,7 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
     if ((rc = upload(ctx->treeMem[11], flat.chunkHi, (const HostF4**)&T.chunkHi, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[12], flat.superLo, (const HostF4**)&T.superLo, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[13], flat.superHi, (const HostF4**)&T.superHi, s))) return fail(rc);
-    T.entryOf = nullptr;
+    T.entryOf = nullptr; T.top = nullptr; T.numTop = 0;
     T.numNodes = flat.numNodes; T.numTris = flat.numTris; T.numRefNodes = flat.numNodes;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = flat.rootLo[a]; T.rootHi[a] = flat.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = flat.tagCand[k];
@@ -204,6 +204,10 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
         if ((rc = upload(ctx->treeMem[20], flat.xsuperLo, (const HostF4**)&X.superLo, s))) return fail(rc);
         if ((rc = upload(ctx->treeMem[21], flat.xsuperHi, (const HostF4**)&X.superHi, s))) return fail(rc);
         if ((rc = upload(ctx->treeMem[22], flat.entryOf, &X.entryOf, s))) return fail(rc);
+        if (!flat.xtop.empty()) {
+            if ((rc = upload(ctx->treeMem[23], flat.xtop, (const HostNode**)&X.top, s))) return fail(rc);
+            X.numTop = (int)flat.xtop.size();
+        }
         X.numNodes = (int)flat.xnodes.size(); X.numTris = flat.xNumTris;
         { size_t hot = (size_t)flat.xNumTris * 40; X.laneCost32 = hot > ((size_t)4 << 20) ? 192 : (hot > ((size_t)512 << 10) ? 64 : 32); }
         if (const char* e = getenv("KDPT_LANE_COST32")) { int v = atoi(e); if (v > 0) X.laneCost32 = v; }
@@ -325,6 +329,11 @@ int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n
     size_t rb = sizeof(kdpt_ray) * (size_t)n, tb = sizeof(float) * (size_t)n, hb = sizeof(kdpt_hit) * (size_t)n;
     if ((rc = ctx->rays.ensure(rb)) || (rc = ctx->hits.ensure(hb)) || (t_min_in && (rc = ctx->tmin.ensure(tb)))) return rc;
     cudaStream_t s = ctx->stream;
+    // whatever goes wrong below, no copy from / into the caller's buffers may still be in flight when this call returns
+    struct SyncUnlessDone {
+        kdpt_ctx* c; cudaStream_t s; bool done;
+        ~SyncUnlessDone() { if (!done) { if (c->copyIn) cudaStreamSynchronize(c->copyIn); if (c->copyOut) cudaStreamSynchronize(c->copyOut); cudaStreamSynchronize(s); } }
+    } guard{ctx, s, false};
     kdpt_ray* dRays = ctx->rays.as<kdpt_ray>();
     kdpt_hit* dHits = ctx->hits.as<kdpt_hit>();
     float* dTmin = t_min_in ? ctx->tmin.as<float>() : nullptr;
@@ -357,6 +366,7 @@ int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n
     }
     if (slice < n) KDPT_CUDA(cudaStreamSynchronize(ctx->copyOut));
     KDPT_CUDA(cudaStreamSynchronize(s));
+    guard.done = true;
     return KDPT_OK;
 }
 

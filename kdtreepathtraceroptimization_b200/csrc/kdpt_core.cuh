@@ -74,6 +74,8 @@ struct Tree {
     const float4* superLo;   // boxes of groups of 32 chunks (leaves with >= 64 chunks); chunkLo[first].w = first group
     const float4* superHi;
     const int* entryOf;      // refined view only (else NULL): TriBare index -> entry of nrmA/nrmB/nrmC (see below)
+    const uint4* top;        // refined view only: breadth-first copy of the top levels for shared-memory staging (numTop nodes;
+    int numTop;              // children inside the copy are named by position | 0x80000000), see kdpt_lean.cuh
     int numNodes;
     int numTris;
     int numRefNodes;         // nodes[i], i < numRefNodes, are the reference's nodes (both views)
@@ -680,5 +682,206 @@ KDPT_HD void traceRef(const Tree& T, V3 o, V3 d, float tMinIn, Hit& H, float* la
     // failed the second test; nothing ever reads them)
     if (lastBary) { lastBary[0] = bu; lastBary[1] = bv; lastBary[2] = bz; }
 }
+
+#if defined(__CUDACC__)
+// ---- reference-compatible traversal, warp-cooperative leaves ------------------------------------------------------
+// Same walk and same results as traceRef (bit for bit), but a lane that arrives at a leaf of at least kRefCoopMin
+// entries does not loop over it alone: the warp takes such leaves one owner at a time, 32 entries per step (and 32 chunk
+// boxes per step on chunked leaves, line test only — see traceRef), and the order-dependent leaf results are rebuilt by
+// reductions keyed on the entries' TriBare indices: last barycentric-test survivor (max index) -> bary.z, last glm hit
+// (max index) -> material, best nudged t with the smaller index winning ties inside the leaf -> accepted hit, and the
+// number of glm hits -> T2's tag updates. Must be called by all 32 lanes (lanes without a ray pass active = false).
+constexpr int kRefCoopMin = 24;
+template <bool T2>
+__device__ __forceinline__ void traceRefWarp(const Tree& T, bool active, V3 o, V3 d, float tMinIn, Hit& H)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    initHit(H, tMinIn);
+    float bz = FLT_MAX;
+    const float eps = T2 ? 0.0001f : 0.00001f;
+    bool run = active && T.numNodes != 0;
+    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    unsigned tagMask = 0;
+    auto tagged = [&](int id) -> bool {
+        if (!T2 || id < 0) return false;
+        return ((tagMask & 1u) && id == T.tagCand[0]) || ((tagMask & 2u) && id == T.tagCand[1]) ||
+               ((tagMask & 4u) && id == T.tagCand[2]) || ((tagMask & 8u) && id == T.tagCand[3]);
+    };
+    int stNode[kMaxDepth]; int stSecond[kMaxDepth]; float stDist[kMaxDepth];
+    int sp = 0, cur = 0;
+    // the leaf the lane stands at (pending) and what its T2 tag update needs
+    int lstart = 0, lcount = 0, lparent = -1; unsigned lchunk0 = kNoChunks; bool lleftFirst = true;
+    // pop: the next node of the walk, -1 when the ray is finished
+    auto popNext = [&]() -> int {
+        while (sp > 0) {
+            const int n = stNode[sp - 1], sec = stSecond[sp - 1]; const float pd = stDist[sp - 1];
+            if (tagged(n)) { sp--; continue; }
+            if (pd > bz) { sp--; continue; }
+            if (sec != -1 && !tagged(sec)) { stSecond[sp - 1] = -1; return sec; }
+            sp--;
+        }
+        return -1;
+    };
+    // what a leaf did to the ray's order-dependent state, then on with the walk
+    auto afterLeaf = [&](int zOrig, float zNew, int nHits) {
+        if (zOrig >= 0) bz = zNew;
+        if (T2) {
+            for (int h = 0; h < (nHits < 2 ? nHits : 2); h++) {      // "skip other side" (:1136/:1199), saturates after two
+                const int k = tagged(lparent) ? 1 : 0;
+                if (k < T.numNodes) {
+                    const int bit = k * 2 + (lleftFirst ? 1 : 0);
+                    if (T.tagCand[bit] >= 0) tagMask |= 1u << bit;
+                }
+            }
+        }
+        const int nx = popNext();
+        if (nx == -1) run = false; else cur = nx;
+    };
+    while (__any_sync(FULL, run)) {
+        // ---- phase 1 (per lane): walk until the lane stands at a leaf it has to test, or the ray is finished ----
+        bool pending = false;
+        while (run && !pending) {
+            const uint4 nd = __ldg(T.nodes + cur);
+            float dist;
+            const float4 bhi = __ldg(T.boxHi + cur);
+            const bool hitGeom = refBox(o, inv, __ldg(T.boxLo + cur), bhi, dist);
+            if (hitGeom && !(dist > bz)) {
+                const int nodeAxis = __float_as_int(bhi.w);
+                const bool leftFirst = !(T2 && !(comp(d, nodeAxis) > 0.0f));
+                if ((nd.w & 3u) == kLeafFlag) {
+                    lstart = (int)nd.x; lcount = (int)nd.y; lchunk0 = nd.z; lparent = (int)(nd.w >> 2) - 1; lleftFirst = leftFirst;
+                    pending = true;
+                    break;
+                }
+                const int first = leftFirst ? (int)nd.z : (int)nd.y, second = leftFirst ? (int)nd.y : (int)nd.z;
+                const bool fOk = !tagged(first), sOk = !tagged(second);
+                if (fOk) { stNode[sp] = cur; stSecond[sp] = sOk ? second : -1; stDist[sp] = dist; sp++; cur = first; continue; }
+                if (sOk) { stNode[sp] = cur; stSecond[sp] = -1; stDist[sp] = dist; sp++; cur = second; continue; }
+            }
+            const int nx = popNext();
+            if (nx == -1) run = false; else cur = nx;
+        }
+        // ---- phase 2 (whole warp): the big pending leaves, one owner at a time ----
+        unsigned big = __ballot_sync(FULL, pending && lcount >= kRefCoopMin);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const V3 O = mk(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
+            const V3 D = mk(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
+            const V3 INV = mk(__shfl_sync(FULL, inv.x, src), __shfl_sync(FULL, inv.y, src), __shfl_sync(FULL, inv.z, src));
+            const int cstart = __shfl_sync(FULL, lstart, src), ccount = __shfl_sync(FULL, lcount, src);
+            const unsigned cchunk0 = __shfl_sync(FULL, lchunk0, src);
+            const float bestT = __shfl_sync(FULL, H.t, src);
+            // lane-local results over the entries this lane tests
+            int zOrig = -1; float zz = 0.f, zu = 0.f, zv = 0.f;
+            int mOrig = -1, mMtl = -1, nHits = 0, accOrig = -1;
+            Hit L; L.t = bestT; L.tri = -1; L.z = L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
+            auto testEntry = [&](int i) {
+                const TriHot tr = loadTri(T, i);
+                float u, v, z;
+                const int r = rayTri(O, D, tr.v0, tr.e1, tr.e2, u, v, z);
+                if (r == 0) return;
+                const int orig = __ldg(T.triOrig + i);
+                if (orig > zOrig) { zOrig = orig; zz = z; zu = u; zv = v; }
+                if (r == 2) {
+                    nHits++;
+                    if (acceptHit(T, i, tr.canon, O, D, u, v, z, eps, orig, accOrig, L)) accOrig = orig;
+                    if (orig > mOrig) { mOrig = orig; mMtl = __float_as_int(__ldg(T.nrmC + i).y); }
+                }
+            };
+            if (cchunk0 == kNoChunks) {
+                for (int k = (int)lane; k < ccount; k += 32) testEntry(cstart + k);
+            } else {
+                const int nch = (ccount + 31) >> 5;
+                auto chunkGroup = [&](int cb) {
+                    const int c = cb + (int)lane;
+                    bool may = false;
+                    if (c < nch) { float tn, tf; chunkInterval(T, (int)cchunk0 + c, O, INV, tn, tf); may = !(tn > tf); }
+                    unsigned hitMask = __ballot_sync(FULL, may);
+                    while (hitMask) {
+                        const int j = __ffs(hitMask) - 1;
+                        hitMask &= hitMask - 1;
+                        const int k = (cb + j) * 32 + (int)lane;
+                        if (k < ccount) testEntry(cstart + k);
+                    }
+                };
+                const int sup0 = superFirst(T, cchunk0);
+                if (sup0 < 0) {
+                    for (int cb = 0; cb < nch; cb += 32) chunkGroup(cb);
+                } else {
+                    const int nsup = (nch + 31) >> 5;
+                    for (int sb = 0; sb < nsup; sb += 32) {
+                        const int g = sb + (int)lane;
+                        bool may = false;
+                        if (g < nsup) { float tn, tf; boxInterval(T.superLo, T.superHi, sup0 + g, O, INV, tn, tf); may = !(tn > tf); }
+                        unsigned gm = __ballot_sync(FULL, may);
+                        while (gm) {
+                            const int j = __ffs(gm) - 1;
+                            gm &= gm - 1;
+                            chunkGroup((sb + j) * 32);
+                        }
+                    }
+                }
+            }
+            // reductions: last bary writer, last glm hit, accepted hit, hit count
+            const int zWin = __reduce_max_sync(FULL, zOrig);
+            const int mWin = __reduce_max_sync(FULL, mOrig);
+            const int hitsAll = __reduce_add_sync(FULL, nHits);
+            float rz = 0.f; int rm = -1;
+            if (zWin >= 0) {
+                const int wl = __ffs(__ballot_sync(FULL, zOrig == zWin)) - 1;
+                rz = __shfl_sync(FULL, zz, wl);
+            }
+            if (mWin >= 0) {
+                const int wl = __ffs(__ballot_sync(FULL, mOrig == mWin)) - 1;
+                rm = __shfl_sync(FULL, mMtl, wl);
+            }
+            // accepted: min t, ties to the smaller TriBare index
+            float kt = accOrig >= 0 ? L.t : FLT_MAX; int ko = accOrig >= 0 ? accOrig : 0x7fffffff;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float t2 = __shfl_xor_sync(FULL, kt, off); const int o2 = __shfl_xor_sync(FULL, ko, off);
+                if (t2 < kt || (t2 == kt && o2 < ko)) { kt = t2; ko = o2; }
+            }
+            const bool anyAcc = ko != 0x7fffffff;
+            Hit W = L;
+            if (anyAcc) {
+                const int wl = __ffs(__ballot_sync(FULL, accOrig >= 0 && L.t == kt && accOrig == ko)) - 1;
+                W.t = kt;
+                W.z = __shfl_sync(FULL, L.z, wl); W.u = __shfl_sync(FULL, L.u, wl); W.v = __shfl_sync(FULL, L.v, wl);
+                W.tri = __shfl_sync(FULL, L.tri, wl);
+                W.nx = __shfl_sync(FULL, L.nx, wl); W.ny = __shfl_sync(FULL, L.ny, wl); W.nz = __shfl_sync(FULL, L.nz, wl);
+                W.mtl = __shfl_sync(FULL, L.mtl, wl);
+            }
+            if ((int)lane == src) {
+                if (anyAcc) { H.t = W.t; H.z = W.z; H.u = W.u; H.v = W.v; H.tri = W.tri; H.nx = W.nx; H.ny = W.ny; H.nz = W.nz; H.mtl = W.mtl; }
+                if (mWin >= 0) H.anyMtl = rm;
+                pending = false;
+                afterLeaf(zWin, rz, hitsAll);
+            }
+        }
+        // ---- phase 3 (per lane): small leaves stay lane-private ----
+        if (pending) {
+            int zOrig = -1, mtlOrig = -1, accOrig = -1, nHits = 0;
+            float zNew = bz;
+            for (int i = lstart; i < lstart + lcount; i++) {
+                const TriHot tr = loadTri(T, i);
+                float u, v, z;
+                const int r = rayTri(o, d, tr.v0, tr.e1, tr.e2, u, v, z);
+                if (r == 0) continue;
+                const int orig = __ldg(T.triOrig + i);
+                if (orig > zOrig) { zOrig = orig; zNew = z; }
+                if (r == 2) {
+                    nHits++;
+                    if (acceptHit(T, i, tr.canon, o, d, u, v, z, eps, orig, accOrig, H)) accOrig = orig;
+                    if (orig > mtlOrig) { mtlOrig = orig; H.anyMtl = __float_as_int(__ldg(T.nrmC + i).y); }
+                }
+            }
+            afterLeaf(zOrig, zNew, nHits);
+        }
+    }
+}
+#endif // __CUDACC__
 
 } // namespace kdpt

@@ -328,6 +328,7 @@ FlattenOpts::FlattenOpts()
 {
     if (const char* e = getenv("KDPT_REFINE_LEAF")) refineLeafMax = atoi(e);
     if (const char* e = getenv("KDPT_REFINE_CT")) traversalCost = (float)atof(e);
+    if (const char* e = getenv("KDPT_TOP_LEVELS")) topLevels = atoi(e);
 }
 
 bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, FlatTree& out,
@@ -514,6 +515,29 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
         fillHot(xorder, tris, canon, nthreads, out.xtriA, out.xtriB, out.xtriC);
         out.entryOf.resize(numTris);
         parallelFor(numTris, nthreads, [&](int lo, int hi) { for (int i = lo; i < hi; i++) out.entryOf[order[i]] = i; });
+        if (opts.topLevels > 0) {
+            // breadth-first copy of the first topLevels levels (at most 2^levels - 1 nodes)
+            const int levels = opts.topLevels > 11 ? 11 : opts.topLevels;
+            std::vector<uint32_t> ids{0u}; std::vector<int> lvl{0};
+            for (size_t q = 0; q < ids.size(); q++) {
+                const HostNode& h = out.xnodes[ids[q]];
+                if ((h.w & 3u) == 3u || lvl[q] + 1 >= levels) continue;
+                ids.push_back(h.z); lvl.push_back(lvl[q] + 1);
+                ids.push_back(h.y); lvl.push_back(lvl[q] + 1);
+            }
+            std::unordered_map<uint32_t, uint32_t> pos;
+            for (size_t q = 0; q < ids.size(); q++) pos[ids[q]] = (uint32_t)q;
+            out.xtop.resize(ids.size());
+            for (size_t q = 0; q < ids.size(); q++) {
+                HostNode h = out.xnodes[ids[q]];
+                if ((h.w & 3u) != 3u) {
+                    auto a = pos.find(h.y), b = pos.find(h.z);
+                    if (a != pos.end()) h.y = a->second | 0x80000000u;
+                    if (b != pos.end()) h.z = b->second | 0x80000000u;
+                }
+                out.xtop[q] = h;
+            }
+        }
     }
     return true;
 }

@@ -33,6 +33,9 @@ struct FlatTree {
     BulkVector<HostF4> xtriA, xtriB;
     BulkVector<HostF2> xtriC;
     std::vector<HostF4> xchunkLo, xchunkHi, xsuperLo, xsuperHi;
+    // the top levels of the refined tree in breadth-first order, for the kernels' shared-memory copy: same record, but a
+    // child that is itself in this array is named by (its position | 0x80000000), any other child by its xnodes index
+    std::vector<HostNode> xtop;
     BulkVector<int> entryOf;                    // TriBare index -> entry of triA/.../nrmC holding it (inverse of triOrig)
     int xNumTris = 0, xMaxDepth = 0, xMaxLeaf = 0;
     float rootLo[3] = {0, 0, 0}, rootHi[3] = {0, 0, 0};
@@ -42,8 +45,9 @@ struct FlatTree {
 };
 
 struct FlattenOpts {
-    int refineLeafMax = 4;      // leaves with more triangles than this are split further for the exact modes; 0 = off
-    float traversalCost = 1.0f; // SAH: cost of one node step relative to one triangle test
+    int refineLeafMax = 8;      // leaves with more triangles than this are split further for the exact modes; 0 = off
+    float traversalCost = 2.0f; // SAH: cost of one node step relative to one triangle test
+    int topLevels = 0;          // levels of the refined tree copied breadth-first for shared-memory staging (0 = none, <= 11)
     FlattenOpts();              // defaults, overridable in development by KDPT_REFINE_LEAF / KDPT_REFINE_CT
 };
 

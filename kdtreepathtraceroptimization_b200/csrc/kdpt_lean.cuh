@@ -25,11 +25,42 @@ namespace kdpt {
 #define KDPT_LEAN_SMEM_STACK 12
 #endif
 #ifndef KDPT_LEAN_REFILL_MIN
-#define KDPT_LEAN_REFILL_MIN 1      // idle lanes needed before the warp fetches new rays (while rays are left)
+#define KDPT_LEAN_REFILL_MIN 8      // idle lanes needed before the warp fetches new rays (while rays are left): the fetch
+                                    // code runs with only the idle lanes active (1 / 4 / 8: 1623 / 1695 / 1722 Mrays/s on dragon1m)
 #endif
 constexpr int kLeanThreads = KDPT_LEAN_THREADS;
 constexpr int kLeanSmemStack = KDPT_LEAN_SMEM_STACK;
 constexpr int kLeanRing = 8;        // RESTART: entries in the ring
+#ifndef KDPT_TOP_MAX_LEVELS
+#define KDPT_TOP_MAX_LEVELS 0       // compile-time bound of the shared-memory copy of the tree's top levels (0: not compiled in)
+#endif
+constexpr int kTopMaxNodes = KDPT_TOP_MAX_LEVELS > 0 ? (1 << KDPT_TOP_MAX_LEVELS) - 1 : 1;
+constexpr unsigned kTopFlag = 0x80000000u;
+
+// the block's copy of the top levels (Tree::top); call from every thread of the block before the first round
+__device__ __forceinline__ void leanStageTop(const Tree& T, uint4* sTop)
+{
+#if KDPT_TOP_MAX_LEVELS > 0
+    const int m = T.numTop < kTopMaxNodes ? T.numTop : 0;       // a copy that does not fit is not used at all
+    for (int k = threadIdx.x; k < m; k += blockDim.x) sTop[k] = __ldg(T.top + k);
+    __syncthreads();
+#endif
+}
+__device__ __forceinline__ unsigned leanRoot(const Tree& T)
+{
+#if KDPT_TOP_MAX_LEVELS > 0
+    return (T.numTop > 0 && T.numTop < kTopMaxNodes) ? kTopFlag : 0u;
+#else
+    return 0u;
+#endif
+}
+__device__ __forceinline__ uint4 leanNode(const Tree& T, const uint4* sTop, unsigned cur)
+{
+#if KDPT_TOP_MAX_LEVELS > 0
+    if (cur & kTopFlag) return sTop[cur & ~kTopFlag];
+#endif
+    return __ldg(T.nodes + cur);
+}
 
 struct HitCand { float t, nx, ny, nz; int mtl; };
 // interpolated normal, nudged point and its distance (pathtrace.cu:993-998) of a triangle glm accepted: the rare part of
@@ -63,7 +94,7 @@ struct LeanState {
 __device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinIn, LeanState& S, Hit& H)
 {
     initHit(H, tMinIn);
-    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = 0; S.li = 0; S.le = 0;
+    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = leanRoot(T); S.li = 0; S.le = 0;
     if (T.numNodes == 0) return false;
     const float len = length(d);
     if (!(len > 0.0f) || !(len <= FLT_MAX)) return false;
@@ -79,7 +110,7 @@ __device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinI
 
 // the leaf at hand is done: take the next pending subtree — it begins where this leaf's cell ends. false = ray finished.
 template <bool RESTART>
-__device__ __forceinline__ bool leanPop(LeanState& S, const Hit& H, const uint2* sStack, const uint2* lStack)
+__device__ __forceinline__ bool leanPop(const Tree& T, LeanState& S, const Hit& H, const uint2* sStack, const uint2* lStack)
 {
     const float tmax = S.tmax;
     const float zb = (H.tri >= 0 ? fminf(H.z, S.zbound) : S.zbound) + S.slack;
@@ -93,23 +124,26 @@ __device__ __forceinline__ bool leanPop(LeanState& S, const Hit& H, const uint2*
         return true;
     }
     if (RESTART && S.dropped && !(tmax >= S.t1 || tmax > zb)) {      // kd-restart: everything up to the exit of this leaf is done
-        S.cur = 0; S.tmin = tmax; S.tmax = S.t1; S.ringBase = 0; S.dropped = false;
+        S.cur = leanRoot(T); S.tmin = tmax; S.tmax = S.t1; S.ringBase = 0; S.dropped = false;
         return true;
     }
     return false;
 }
 
+// glm accepted entry i (canonical index canon): nudged distance, then the reference's acceptance rule
+__device__ __forceinline__ void leanAccept(const Tree& T, const LeanState& S, Hit& H, float eps, int i, int canon, float u, float v, float z)
+{
+    const int ni = T.entryOf ? __ldg(T.entryOf + canon) : i;
+    const HitCand hc = nudgedHit(T.nrmA, T.nrmB, T.nrmC, ni, S.o.x, S.o.y, S.o.z, S.d.x, S.d.y, S.d.z, u, v, z, eps);
+    if (hc.t > 0.0f && (H.t > hc.t || (H.t == hc.t && H.tri >= 0 && canon < H.tri))) {
+        H.t = hc.t; H.z = z; H.u = u; H.v = v; H.tri = canon; H.nx = hc.nx; H.ny = hc.ny; H.nz = hc.nz; H.mtl = hc.mtl;
+    }
+}
 __device__ __forceinline__ void leanTestTri(const Tree& T, const LeanState& S, Hit& H, float eps, int i)
 {
     const TriHot tr = loadTri(T, i);
     float u, v, z;
-    if (rayTriHit(S.o, S.d, tr.v0, tr.e1, tr.e2, u, v, z)) {
-        const int ni = T.entryOf ? __ldg(T.entryOf + tr.canon) : i;
-        const HitCand hc = nudgedHit(T.nrmA, T.nrmB, T.nrmC, ni, S.o.x, S.o.y, S.o.z, S.d.x, S.d.y, S.d.z, u, v, z, eps);
-        if (hc.t > 0.0f && (H.t > hc.t || (H.t == hc.t && H.tri >= 0 && tr.canon < H.tri))) {
-            H.t = hc.t; H.z = z; H.u = u; H.v = v; H.tri = tr.canon; H.nx = hc.nx; H.ny = hc.ny; H.nz = hc.nz; H.mtl = hc.mtl;
-        }
-    }
+    if (rayTriHit(S.o, S.d, tr.v0, tr.e1, tr.e2, u, v, z)) leanAccept(T, S, H, eps, i, tr.canon, u, v, z);
 }
 
 // a leaf the refinement could not split (>= 128 coincident triangles): all of it at once, through its chunk boxes.
@@ -153,7 +187,8 @@ static __device__ __noinline__ Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V
 // the kind more of its lanes are waiting for; the others keep their state and wait for a round of their kind.
 // Returns whether the lane still has a ray.
 template <bool RESTART>
-__device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack)
+__device__ __forceinline__ bool leanRoundUnit(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
+                                          const uint4* sTop)
 {
     const bool inLeaf = alive && S.li < S.le;
     const unsigned leafMask = __ballot_sync(0xffffffffu, inLeaf);
@@ -161,12 +196,12 @@ __device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& 
     if (__popc(leafMask) * KDPT_LEAN_NODE_WEIGHT > __popc(nodeMask) * KDPT_LEAN_LEAF_WEIGHT) {
         if (inLeaf) {
             leanTestTri(T, S, H, eps, S.li);
-            if (++S.li == S.le) alive = leanPop<RESTART>(S, H, sStack, lStack);
+            if (++S.li == S.le) alive = leanPop<RESTART>(T, S, H, sStack, lStack);
         }
         return alive;
     }
     if (alive && !inLeaf) {
-        const uint4 nd = __ldg(T.nodes + S.cur);
+        const uint4 nd = leanNode(T, sTop, S.cur);
         if ((nd.w & 3u) != kLeafFlag) {
             const int a = (int)(nd.w & 3u);
             const float split = __int_as_float((int)nd.x);
@@ -196,11 +231,84 @@ __device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& 
                     const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
                     H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
                 }
-                alive = leanPop<RESTART>(S, H, sStack, lStack);
+                alive = leanPop<RESTART>(T, S, H, sStack, lStack);
             }
         }
     }
     return alive;
+}
+
+#ifndef KDPT_LEAN_TRI_UNROLL
+#define KDPT_LEAN_TRI_UNROLL 1      // triangles of a leaf tested per loop trip (their loads are issued together)
+#endif
+// "while-while" round: the lane descends to its next leaf, tests all of it, pops. The lanes of a warp wait for the longest
+// descent and the fullest leaf among them (measured on dragon_5: 6 of 32 lanes active per instruction), but a lane's own
+// instruction stream is minimal; this is the form that measured fastest (profiles/r2_lean_variants.txt).
+template <bool RESTART>
+__device__ __forceinline__ bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
+                                              const uint4* sTop)
+{
+    if (!alive) return false;
+    unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
+    uint4 nd = leanNode(T, sTop, cur);
+    while ((nd.w & 3u) != kLeafFlag) {
+        const int a = (int)(nd.w & 3u);
+        const float split = __int_as_float((int)nd.x);
+        const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+        const bool below = oa < split || (oa == split && da <= 0.0f);
+        const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+        const float tp = (split - oa) * ia;
+        if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
+        else if (tp <= tmin) cur = farc;
+        else {
+            const uint2 e = make_uint2(farc, __float_as_uint(tmax));
+            if (RESTART) {
+                if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
+                sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
+            } else {
+                if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
+                else lStack[S.sp - kLeanSmemStack] = e;
+            }
+            S.sp++;
+            cur = nearc; tmax = tp;
+        }
+        nd = leanNode(T, sTop, cur);
+    }
+    S.tmax = tmax;
+    const int start = (int)nd.x, count = (int)nd.y;
+    if (count > 0) {
+        if (nd.z == kNoChunks) {
+            int i = start;
+            const int e = start + count;
+#if KDPT_LEAN_TRI_UNROLL >= 2
+            for (; i + 1 < e; i += 2) {
+                const TriHot ta = loadTri(T, i), tb = loadTri(T, i + 1);
+                float u, v, z;
+                if (rayTriHit(S.o, S.d, ta.v0, ta.e1, ta.e2, u, v, z)) leanAccept(T, S, H, eps, i, ta.canon, u, v, z);
+                if (rayTriHit(S.o, S.d, tb.v0, tb.e1, tb.e2, u, v, z)) leanAccept(T, S, H, eps, i + 1, tb.canon, u, v, z);
+            }
+#endif
+            for (; i < e; i++) leanTestTri(T, S, H, eps, i);
+        } else {
+            const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
+            H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
+        }
+    }
+    return leanPop<RESTART>(T, S, H, sStack, lStack);
+}
+
+#ifndef KDPT_LEAN_V
+#define KDPT_LEAN_V 1       // 1: leanRoundLeaf (whole leaf per round), 2: leanRoundUnit (one node step or one triangle per round)
+#endif
+template <bool RESTART>
+__device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
+                                          const uint4* sTop)
+{
+#if KDPT_LEAN_V == 2
+    return leanRoundUnit<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
+#else
+    return leanRoundLeaf<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
+#endif
 }
 
 } // namespace kdpt

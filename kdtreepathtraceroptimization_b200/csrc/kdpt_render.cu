@@ -360,10 +360,8 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
             initHit(H, w.tMin);
             if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, have, w.r.o, w.r.d, w.tMin, 0.00001f, H);
             else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, have, w.r.o, w.r.d, w.tMin, 0.0001f, H);
-            else if (have) {
-                if (MODE == KDPT_REF_T1) traceRef<false>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
-                else traceRef<true>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
-            }
+            else if (MODE == KDPT_REF_T1) traceRefWarp<false>(T, have, w.r.o, w.r.d, w.tMin, H);
+            else traceRefWarp<true>(T, have, w.r.o, w.r.d, w.tMin, H);
             if (have) {
                 w.r.inside = def[7][e] != 0.0f; w.r.sdepth = def[8][e];
                 w.cp = make_float4(def[9][e], def[10][e], def[11][e], def[12][e]);
@@ -496,10 +494,8 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
                     def[11][lane] = w.normal.x; def[12][lane] = w.normal.y; def[13][lane] = w.normal.z;
                     if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.00001f, H);
                     else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.0001f, H);
-                    else if (needTrav) {
-                        if (MODE == KDPT_REF_T1) traceRef<false>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
-                        else traceRef<true>(T, w.r.o, w.r.d, w.tMin, H, nullptr);
-                    }
+                    else if (MODE == KDPT_REF_T1) traceRefWarp<false>(T, needTrav, w.r.o, w.r.d, w.tMin, H);
+                    else traceRefWarp<true>(T, needTrav, w.r.o, w.r.d, w.tMin, H);
                     w.cp = make_float4(def[0][lane], def[1][lane], def[2][lane], def[3][lane]);
                     w.bm = make_int2(__float_as_int(def[4][lane]), __float_as_int(def[5][lane])); w.r.sdepth = def[6][lane];
                     w.hitGeom = __float_as_int(def[7][lane]);
@@ -609,6 +605,8 @@ traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps)
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     __shared__ uint2 sStackAll[(RESTART ? kLeanRing : kLeanSmemStack) * kLeanThreads];
+    __shared__ uint4 sTop[kTopMaxNodes];
+    leanStageTop(T, sTop);
     uint2* sStack = sStackAll + threadIdx.x;
     uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
     const unsigned n = st->gqCount[depth];
@@ -641,7 +639,7 @@ traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps)
         }
         if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
         const bool was = alive;
-        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack);
+        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
         if (was && !alive) store(slot);
     }
 }

@@ -74,10 +74,8 @@ traceKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__
         Hit H;
         if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kCoopMin>(T, active, o, d, tin, 0.00001f, H);
         else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kCoopMin>(T, active, o, d, tin, 0.0001f, H);
-        else if (active) {
-            if (MODE == KDPT_REF_T1) traceRef<false>(T, o, d, tin, H, nullptr);
-            else traceRef<true>(T, o, d, tin, H, nullptr);
-        }
+        else if (MODE == KDPT_REF_T1) traceRefWarp<false>(T, active, o, d, tin, H);
+        else traceRefWarp<true>(T, active, o, d, tin, H);
         if (active) {
             float4* out = reinterpret_cast<float4*>(hits + i);
             out[0] = make_float4(H.t, H.z, H.u, H.v);
@@ -98,6 +96,8 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     __shared__ uint2 sStackAll[(RESTART ? kLeanRing : kLeanSmemStack) * kLeanThreads];
+    __shared__ uint4 sTop[kTopMaxNodes];
+    leanStageTop(T, sTop);
     uint2* sStack = sStackAll + threadIdx.x;
     uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
     LeanState S; Hit H;
@@ -130,7 +130,7 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
         }
         if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
         const bool was = alive;
-        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack);
+        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
         if (was && !alive) {
             float4* out = reinterpret_cast<float4*>(hits + ray);
             out[0] = make_float4(H.t, H.z, H.u, H.v);

@@ -93,23 +93,44 @@ static bool writeHdr(const char* path, const float* rgb, int w, int h)
     return true;
 }
 
-// checkpoint of a long render: "KDPTCKP1", W, H, samples rendered so far, W*H*3 floats (the accumulation buffer)
-static bool writeCheckpoint(const std::string& path, const std::vector<float>& img, int w, int h, int samples)
+// what a checkpoint belongs to: the scene arrays (sizes, the small arrays whole, the ends of the two big ones), the camera
+// and the render parameters. A checkpoint of another scene, resolution, mode or parameter set must not be blended in.
+static uint64_t renderKey(const kdpt_scene& sc, const kdpt_params& p)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto add = [&](const void* ptr, size_t n) { const unsigned char* b = (const unsigned char*)ptr; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+    auto addEnds = [&](const void* ptr, size_t n) { const size_t k = n < (1u << 16) ? n : (1u << 16); add(ptr, k); add((const char*)ptr + (n - k), k); };
+    const int sizes[6] = {sc.numNodes, sc.numTris, sc.numGeoms, sc.numMaterials, sc.numShapes, sc.traceDepth};
+    add(sizes, sizeof sizes);
+    if (sc.numNodes) addEnds(sc.nodes, sizeof(kdpt_node_bare) * (size_t)sc.numNodes);
+    if (sc.numTris) addEnds(sc.tris, sizeof(kdpt_tri_bare) * (size_t)sc.numTris);
+    if (sc.numGeoms) add(sc.geoms, sizeof(kdpt_geom) * (size_t)sc.numGeoms);
+    if (sc.numMaterials) add(sc.materials, sizeof(kdpt_material) * (size_t)sc.numMaterials);
+    add(&sc.camera, sizeof sc.camera);
+    kdpt_params q = p; q.testingmode = 0; q.laneQueue = 0;       // tuning / timing switches do not change the image
+    add(&q, sizeof q);
+    return h;
+}
+
+// checkpoint of a long render: "KDPTCKP2", W, H, samples rendered so far, render key, W*H*3 floats (the accumulation buffer)
+static bool writeCheckpoint(const std::string& path, const std::vector<float>& img, int w, int h, int samples, uint64_t key)
 {
     const std::string tmp = path + ".tmp";
     FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) return false;
     const int hdr[3] = {w, h, samples};
-    bool ok = fwrite("KDPTCKP1", 1, 8, f) == 8 && fwrite(hdr, sizeof(int), 3, f) == 3 && fwrite(img.data(), sizeof(float), img.size(), f) == img.size();
+    bool ok = fwrite("KDPTCKP2", 1, 8, f) == 8 && fwrite(hdr, sizeof(int), 3, f) == 3 && fwrite(&key, sizeof key, 1, f) == 1 &&
+              fwrite(img.data(), sizeof(float), img.size(), f) == img.size();
     ok = fclose(f) == 0 && ok;
     return ok && rename(tmp.c_str(), path.c_str()) == 0;
 }
-static bool readCheckpoint(const std::string& path, std::vector<float>& img, int w, int h, int* samples)
+static bool readCheckpoint(const std::string& path, std::vector<float>& img, int w, int h, int* samples, uint64_t key)
 {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) return false;
-    char magic[8]; int hdr[3];
-    bool ok = fread(magic, 1, 8, f) == 8 && !memcmp(magic, "KDPTCKP1", 8) && fread(hdr, sizeof(int), 3, f) == 3 && hdr[0] == w && hdr[1] == h && hdr[2] >= 0;
+    char magic[8]; int hdr[3]; uint64_t k = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && !memcmp(magic, "KDPTCKP2", 8) && fread(hdr, sizeof(int), 3, f) == 3 && hdr[0] == w && hdr[1] == h && hdr[2] >= 0 &&
+              fread(&k, sizeof k, 1, f) == 1 && k == key;
     if (ok) { img.resize((size_t)w * h * 3); ok = fread(img.data(), sizeof(float), img.size(), f) == img.size(); }
     fclose(f);
     if (ok) *samples = hdr[2];
@@ -176,9 +197,14 @@ int main(int argc, char** argv)
     kdpt_ctx* ctx = nullptr;
     if (kdpt_create(&sc, device, &ctx)) return fail("create");
     kdpt_render_stats st; memset(&st, 0, sizeof st);
+    const uint64_t key = renderKey(sc, p);
     std::vector<float> img((size_t)W * H * 3);
     if (!resume.empty()) {       // the reference cannot do this: its buffer is lost with the process
-        if (!readCheckpoint(resume, img, W, H, &done)) { fprintf(stderr, "kdpt_render: %s is not a checkpoint of a %dx%d render\n", resume.c_str(), W, H); return 1; }
+        if (!readCheckpoint(resume, img, W, H, &done, key)) {
+            fprintf(stderr, "kdpt_render: %s is not a checkpoint of this %dx%d render (scene, camera and parameters must match)\n", resume.c_str(), W, H);
+            return 1;
+        }
+        if (done > spp) { fprintf(stderr, "kdpt_render: %s already holds %d samples, more than --spp %d\n", resume.c_str(), done, spp); return 1; }
         if (kdpt_set_image(ctx, img.data())) return fail("set_image");
     }
     // iterations done+1 .. spp, in slices when checkpoints are wanted (iteration numbers seed the RNG, so a resumed
@@ -191,12 +217,12 @@ int main(int argc, char** argv)
         done += n;
         if (!ckpt.empty()) {
             if (kdpt_get_image(ctx, img.data())) return fail("get_image");
-            if (!writeCheckpoint(ckpt, img, W, H, done)) { fprintf(stderr, "kdpt_render: cannot write %s\n", ckpt.c_str()); return 1; }
+            if (!writeCheckpoint(ckpt, img, W, H, done, key)) { fprintf(stderr, "kdpt_render: cannot write %s\n", ckpt.c_str()); return 1; }
         }
     }
     if (kdpt_get_image(ctx, img.data())) return fail("get_image");
     if (!out.empty()) {
-        const float samples = (float)(spp > 0 ? spp : 1);
+        const float samples = (float)(done > 0 ? done : 1);       // the samples actually accumulated
         bool pfm = out.size() > 4 && out.substr(out.size() - 4) == ".pfm";
         bool ppm = out.size() > 4 && out.substr(out.size() - 4) == ".ppm";
         bool hdr = out.size() > 4 && out.substr(out.size() - 4) == ".hdr";

@@ -28,7 +28,7 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
     T.nrmA = (const float4*)F.nrmA.data(); T.nrmB = (const float4*)F.nrmB.data(); T.nrmC = (const float2*)F.nrmC.data();
     T.triOrig = F.triOrig.data(); T.chunkLo = (const float4*)F.chunkLo.data(); T.chunkHi = (const float4*)F.chunkHi.data();
     T.superLo = (const float4*)F.superLo.data(); T.superHi = (const float4*)F.superHi.data();
-    T.entryOf = nullptr;
+    T.entryOf = nullptr; T.top = nullptr; T.numTop = 0;
     T.numNodes = F.numNodes; T.numTris = F.numTris; T.numRefNodes = F.numNodes;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = F.rootLo[a]; T.rootHi[a] = F.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = F.tagCand[k];

@@ -252,6 +252,11 @@ def test_headless_cli_checkpoint_resume_cache_and_hdr(tmp_path):
     assert part["ray_bounces"] + rest["ray_bounces"] == full["ray_bounces"]
     r = subprocess.run(base + ["--spp", "10", "--res", "64x64", "--resume", str(tmp_path / "part.ckp")], capture_output=True, text=True)
     assert r.returncode != 0 and "not a checkpoint" in r.stderr                    # other resolution
+    other = [a if a != "shortstack" else "fullstack" for a in base]
+    r = subprocess.run(other + ["--spp", "10", "--resume", str(tmp_path / "part.ckp")], capture_output=True, text=True)
+    assert r.returncode != 0 and "not a checkpoint" in r.stderr                    # other render parameters
+    r = subprocess.run(base + ["--spp", "3", "--resume", str(tmp_path / "part.ckp")], capture_output=True, text=True)
+    assert r.returncode != 0 and "already holds" in r.stderr                       # more samples in the file than asked for
     run("--spp", "10", "--resume", str(tmp_path / "full.ckp"), "--out", str(tmp_path / "img.hdr"))   # nothing left to render
     raw = (tmp_path / "img.hdr").read_bytes()
     head = b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 60 +X 80\n"
