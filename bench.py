@@ -58,7 +58,7 @@ TRACE_WORKLOADS = {
 DEFAULT_WORKLOAD = "dragon1m"
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 L2_BYTES = 126.5e6          # cudaDeviceProp::l2CacheSize on this pool's B200 (profiles/r1_l2_peak.json)
-MODE_NAMES = {"fullstack": 0, "shortstack": 1, "ref_t1": 2, "ref_t2": 3}
+MODE_NAMES = {"fullstack": 0, "shortstack": 1, "ref_t1": 2, "ref_t2": 3, "brute": 4, "brute_bbox": 5}
 
 
 def P(a):
@@ -216,7 +216,7 @@ def cpu_iteration_runner(sc, params):
             R = None
     img = np.zeros((n, 3), 'f4')
     # the reference has only its two lossy traversals; fullstack/ref_t1 -> traverseKDbare, shortstack/ref_t2 -> ShortHybrid
-    shortstack = 1 if params.mode in (1, 3) else 0
+    shortstack = 1 if params.mode in (1, 3, 4, 5) else 0
     paths = np.zeros(n, KO_PATH)
 
     def run(it, stride=1, threads=None):
@@ -439,7 +439,7 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (reference-compatible mode line)")
-    ap.add_argument("--mode", default=None, choices=["fullstack", "shortstack", "ref_t1", "ref_t2"],
+    ap.add_argument("--mode", default=None, choices=["fullstack", "shortstack", "ref_t1", "ref_t2", "brute", "brute_bbox"],
                     help="override the workload's traversal mode")
     args = ap.parse_args()
     if args.steps is None:

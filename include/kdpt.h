@@ -87,7 +87,12 @@ typedef enum {
     /* bit-compatible with the reference's own (lossy) functions, including the hits they drop */
     KDPT_REF_T1 = 2,        /* traverseKDbare,            pathtrace.cu:881-1020 */
     KDPT_REF_T2 = 3,        /* traverseKDbareShortHybrid, pathtrace.cu:1023-1235 */
-    KDPT_MODE_COUNT = 4
+    /* the reference's KD-less modes (ENABLEKD off, key K; USEBBOX, key B): every triangle against every ray, nudge 1e-4,
+     * pathTraceOneBounce (pathtrace.cu:402-628), with the mesh bounding-box reject of :497-511 in the second form. Same
+     * results as KDPT_SHORTSTACK; they exist for the reference's brute force / bounding box / kd-tree comparison */
+    KDPT_BRUTE = 4,
+    KDPT_BRUTE_BBOX = 5,
+    KDPT_MODE_COUNT = 6
 } kdpt_mode;
 
 /* ---- render loop toggles: the trailing arguments of pathtrace(), src/pathtrace.h:8-21, defaults main.cpp:35-60 */
@@ -105,7 +110,10 @@ typedef struct {
     int laneQueue;          /* tuning, no effect on results: how a bounce traverses the lanes of a 32-path packet that enter
                                the KD tree. 0 = the kernel decides per launch from the measured entering fraction
                                (default), 1 = always at once, 2 = always pooled in the per-warp queue */
-    int reserved[2];
+    int cacheRays;          /* rayCaching (pathtrace.cu:2448-2456, default 0): every iteration starts from iteration 1's camera
+                               rays (no per-iteration antialiasing / depth-of-field jitter); here that is a choice of jitter
+                               constants, the rays are generated inside the first bounce either way */
+    int reserved[1];
 } kdpt_params;
 
 typedef struct {            /* filled by kdpt_render */

@@ -36,8 +36,8 @@ HIT = np.dtype([('t', 'f4'), ('z', 'f4'), ('u', 'f4'), ('v', 'f4'), ('tri', 'i4'
 assert (NODE.itemsize, TRI.itemsize, GEOM.itemsize, MATERIAL.itemsize, CAMERA.itemsize, RAY.itemsize, HIT.itemsize) == \
     (64, 76, 236, 56, 84, 24, 32)
 
-FULLSTACK, SHORTSTACK, REF_T1, REF_T2 = 0, 1, 2, 3
-MODES = {"fullstack": FULLSTACK, "shortstack": SHORTSTACK, "ref_t1": REF_T1, "ref_t2": REF_T2}
+FULLSTACK, SHORTSTACK, REF_T1, REF_T2, BRUTE, BRUTE_BBOX = 0, 1, 2, 3, 4, 5
+MODES = {"fullstack": FULLSTACK, "shortstack": SHORTSTACK, "ref_t1": REF_T1, "ref_t2": REF_T2, "brute": BRUTE, "brute_bbox": BRUTE_BBOX}
 
 
 class KdptError(RuntimeError):
@@ -62,7 +62,7 @@ class CParams(ctypes.Structure):
     _fields_ = [("focalLength", ctypes.c_float), ("dofAngle", ctypes.c_float), ("softness", ctypes.c_float),
                 ("antialias", ctypes.c_int), ("enableSss", ctypes.c_int), ("compaction", ctypes.c_int),
                 ("mode", ctypes.c_int), ("sortByMaterial", ctypes.c_int), ("testingmode", ctypes.c_int),
-                ("laneQueue", ctypes.c_int), ("reserved", ctypes.c_int * 2)]
+                ("laneQueue", ctypes.c_int), ("cacheRays", ctypes.c_int), ("reserved", ctypes.c_int * 1)]
 
 
 class CBuildOpts(ctypes.Structure):

@@ -358,6 +358,67 @@ KDPT_HD void traceExact(const Tree& T, V3 o, V3 d, float tMinIn, float eps, Hit&
 }
 
 #if defined(__CUDACC__)
+// best candidate of the warp (min nudged t, ties to the smaller canonical index) back to the owner lane `src`; L = every
+// lane's local best, started from the owner's (bestT, bestTri)
+__device__ __forceinline__ void warpBestToOwner(int src, float bestT, int bestTri, const Hit& L, Hit& H)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool improved = L.t != bestT || L.tri != bestTri;
+    if (!__ballot_sync(FULL, improved)) return;
+    float kt = improved ? L.t : FLT_MAX; int kc = improved ? L.tri : 0x7fffffff;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        float t2 = __shfl_xor_sync(FULL, kt, off); int c2 = __shfl_xor_sync(FULL, kc, off);
+        if (t2 < kt || (t2 == kt && c2 < kc)) { kt = t2; kc = c2; }
+    }
+    const int win = __ffs(__ballot_sync(FULL, improved && L.t == kt && L.tri == kc)) - 1;
+    Hit W;
+    W.t = kt; W.tri = kc;
+    W.z = __shfl_sync(FULL, L.z, win); W.u = __shfl_sync(FULL, L.u, win); W.v = __shfl_sync(FULL, L.v, win);
+    W.nx = __shfl_sync(FULL, L.nx, win); W.ny = __shfl_sync(FULL, L.ny, win); W.nz = __shfl_sync(FULL, L.nz, win);
+    W.mtl = __shfl_sync(FULL, L.mtl, win); W.anyMtl = W.mtl;
+    if ((int)lane == src) H = W;
+}
+
+// ---- brute force (KDPT_BRUTE / KDPT_BRUTE_BBOX): the reference's KD-less modes, pathTraceOneBounce (pathtrace.cu:402-628)
+// Every TriBare entry is tested for every ray — 32 entries per step by the warp, one owner ray at a time — with the nudge
+// (1e-4) and the acceptance rule of that kernel; BBOX first rejects rays that miss the mesh's bounding box (the
+// reference's per-shape AABB reject, :497-511; here the KD root box, which bounds every triangle). By construction the
+// result is what KDPT_SHORTSTACK returns; the modes exist to reproduce the reference's brute force / bounding box /
+// kd-tree comparison (README, presentation/benchmarks.py) on this hardware.
+template <bool BBOX>
+__device__ __forceinline__ void traceBruteWarp(const Tree& T, bool active, V3 o, V3 d, float tMinIn, float eps, Hit& H)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    initHit(H, tMinIn);
+    bool run = active && T.numTris > 0;
+    if (BBOX && run) {
+        const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        float t0, t1;
+        if (!slab(o, inv, T.rootLo, T.rootHi, t0, t1)) run = false;
+    }
+    unsigned todo = __ballot_sync(FULL, run);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const V3 O = mk(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
+        const V3 D = mk(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
+        const float bestT = __shfl_sync(FULL, H.t, src);
+        const int bestTri = __shfl_sync(FULL, H.tri, src);
+        Hit L; L.t = bestT; L.tri = bestTri; L.z = L.u = L.v = 0.f; L.nx = L.ny = L.nz = 0.f; L.mtl = -1; L.anyMtl = -1;
+        for (int k = (int)lane; k < T.numTris; k += 32) {
+            const TriHot tr = loadTri(T, k);
+            float u, v, z;
+            if (rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, k, tr.canon, O, D, u, v, z, eps, tr.canon, L.tri, L);
+        }
+        warpBestToOwner(src, bestT, bestTri, L, H);
+    }
+}
+#endif
+
+#if defined(__CUDACC__)
 // ---- exact closest hit, warp-cooperative leaves ---------------------------------------------------------------
 // Same traversal as traceExact (so the same leaves and triangles are tested and the same hit is returned), but the
 // reference tree's fat leaves (hundreds of triangles: the builder stops at depth 14) are not walked by one lane while
@@ -406,24 +467,7 @@ __device__ __forceinline__ void traceExactWarp(const Tree& T, bool active, V3 o,
             if (rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z)) acceptHit(T, cstart + k, tr.canon, O, D, u, v, z, eps, tr.canon, L.tri, L);
         }
     };
-    // best candidate of the warp (min nudged t, ties to the smaller canonical index) back to the owner lane
-    auto reduceToOwner = [&](int src, float bestT, int bestTri, const Hit& L) {
-        const bool improved = L.t != bestT || L.tri != bestTri;
-        if (!__ballot_sync(FULL, improved)) return;
-        float kt = improved ? L.t : FLT_MAX; int kc = improved ? L.tri : 0x7fffffff;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            float t2 = __shfl_xor_sync(FULL, kt, off); int c2 = __shfl_xor_sync(FULL, kc, off);
-            if (t2 < kt || (t2 == kt && c2 < kc)) { kt = t2; kc = c2; }
-        }
-        const int win = __ffs(__ballot_sync(FULL, improved && L.t == kt && L.tri == kc)) - 1;
-        Hit W;
-        W.t = kt; W.tri = kc;
-        W.z = __shfl_sync(FULL, L.z, win); W.u = __shfl_sync(FULL, L.u, win); W.v = __shfl_sync(FULL, L.v, win);
-        W.nx = __shfl_sync(FULL, L.nx, win); W.ny = __shfl_sync(FULL, L.ny, win); W.nz = __shfl_sync(FULL, L.nz, win);
-        W.mtl = __shfl_sync(FULL, L.mtl, win); W.anyMtl = W.mtl;
-        if ((int)lane == src) H = W;
-    };
+    auto reduceToOwner = [&](int src, float bestT, int bestTri, const Hit& L) { warpBestToOwner(src, bestT, bestTri, L, H); };
 
     while (__any_sync(FULL, run)) {
         int start = 0, count = 0; unsigned chunk0 = kNoChunks;

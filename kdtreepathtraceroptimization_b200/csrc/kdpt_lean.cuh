@@ -297,15 +297,77 @@ __device__ __forceinline__ bool leanRoundLeaf(const Tree& T, bool alive, LeanSta
     return leanPop<RESTART>(T, S, H, sStack, lStack);
 }
 
-#ifndef KDPT_LEAN_V
-#define KDPT_LEAN_V 1       // 1: leanRoundLeaf (whole leaf per round), 2: leanRoundUnit (one node step or one triangle per round)
+#ifndef KDPT_LEAN_NODE_CAP
+#define KDPT_LEAN_NODE_CAP 8
 #endif
+#ifndef KDPT_LEAN_TRI_CAP
+#define KDPT_LEAN_TRI_CAP 8
+#endif
+// "capped while-while" round: as leanRoundLeaf, but a lane takes at most NODE_CAP node steps and then at most TRI_CAP
+// triangle tests per round and keeps its place (node, or cursor inside the leaf) for the next round. The first descent of a
+// ray crosses ~20 levels, later ones 2-5, and leaves hold 0 to dozens of entries: uncapped, every round lasts as long as
+// the warp's longest descent plus its fullest leaf while the average lane needs a third of either.
+template <bool RESTART>
+__device__ __forceinline__ bool leanRoundCapped(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
+                                                const uint4* sTop)
+{
+    if (!alive) return false;
+    if (S.li >= S.le) {
+        unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
+        uint4 nd = leanNode(T, sTop, cur);
+        int steps = KDPT_LEAN_NODE_CAP;
+        while ((nd.w & 3u) != kLeafFlag) {
+            if (steps-- == 0) { S.cur = cur; S.tmin = tmin; S.tmax = tmax; return true; }      // on with this descent next round
+            const int a = (int)(nd.w & 3u);
+            const float split = __int_as_float((int)nd.x);
+            const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+            const bool below = oa < split || (oa == split && da <= 0.0f);
+            const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+            const float tp = (split - oa) * ia;
+            if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
+            else if (tp <= tmin) cur = farc;
+            else {
+                const uint2 e = make_uint2(farc, __float_as_uint(tmax));
+                if (RESTART) {
+                    if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
+                    sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
+                } else {
+                    if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
+                    else lStack[S.sp - kLeanSmemStack] = e;
+                }
+                S.sp++;
+                cur = nearc; tmax = tp;
+            }
+            nd = leanNode(T, sTop, cur);
+        }
+        S.cur = cur; S.tmin = tmin; S.tmax = tmax;
+        const int start = (int)nd.x, count = (int)nd.y;
+        if (count > 0 && nd.z != kNoChunks) {
+            const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
+            H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
+            return leanPop<RESTART>(T, S, H, sStack, lStack);
+        }
+        if (count <= 0) return leanPop<RESTART>(T, S, H, sStack, lStack);
+        S.li = start; S.le = start + count;
+    }
+    const int e = S.le < S.li + KDPT_LEAN_TRI_CAP ? S.le : S.li + KDPT_LEAN_TRI_CAP;
+    for (int i = S.li; i < e; i++) leanTestTri(T, S, H, eps, i);
+    S.li = e;
+    if (e < S.le) return true;              // the rest of this leaf next round
+    return leanPop<RESTART>(T, S, H, sStack, lStack);
+}
+
+#ifndef KDPT_LEAN_V
+#define KDPT_LEAN_V 1       // 1: leanRoundLeaf (whole leaf per round), 2: leanRoundUnit (one node step or one triangle per round),
+#endif                      // 3: leanRoundCapped
 template <bool RESTART>
 __device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
                                           const uint4* sTop)
 {
 #if KDPT_LEAN_V == 2
     return leanRoundUnit<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
+#elif KDPT_LEAN_V == 3
+    return leanRoundCapped<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
 #else
     return leanRoundLeaf<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
 #endif

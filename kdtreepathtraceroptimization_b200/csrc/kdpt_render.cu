@@ -361,7 +361,9 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
             if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, have, w.r.o, w.r.d, w.tMin, 0.00001f, H);
             else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, have, w.r.o, w.r.d, w.tMin, 0.0001f, H);
             else if (MODE == KDPT_REF_T1) traceRefWarp<false>(T, have, w.r.o, w.r.d, w.tMin, H);
-            else traceRefWarp<true>(T, have, w.r.o, w.r.d, w.tMin, H);
+            else if (MODE == KDPT_REF_T2) traceRefWarp<true>(T, have, w.r.o, w.r.d, w.tMin, H);
+            else if (MODE == KDPT_BRUTE) traceBruteWarp<false>(T, have, w.r.o, w.r.d, w.tMin, 0.0001f, H);
+            else traceBruteWarp<true>(T, have, w.r.o, w.r.d, w.tMin, 0.0001f, H);
             if (have) {
                 w.r.inside = def[7][e] != 0.0f; w.r.sdepth = def[8][e];
                 w.cp = make_float4(def[9][e], def[10][e], def[11][e], def[12][e]);
@@ -437,7 +439,8 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
                     if (tg > 0.0f && w.tMin > tg) { w.tMin = tg; w.hitGeom = g; w.ipoint = pt; w.normal = nr; }
                 }
                 // does the ray reach the tree at all? (the traversals' own first step: a miss of the root box ends them)
-                if (T.numNodes != 0) {
+                if (MODE == KDPT_BRUTE) needTrav = T.numTris > 0;        // every triangle for every ray, no box of any kind
+                else if (T.numNodes != 0) {
                     float t0, t1;
                     needTrav = slab(w.r.o, ginv, T.rootLo, T.rootHi, t0, t1);
                     // exact modes: also done when the box begins beyond the closest geom hit (the kernels' early-exit rule)
@@ -495,7 +498,9 @@ bounceBody(const Tree& T, const SceneView& S, const PathSoA& P, LoopState* st, c
                     if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kBounceCoopMin>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.00001f, H);
                     else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kBounceCoopMin>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.0001f, H);
                     else if (MODE == KDPT_REF_T1) traceRefWarp<false>(T, needTrav, w.r.o, w.r.d, w.tMin, H);
-                    else traceRefWarp<true>(T, needTrav, w.r.o, w.r.d, w.tMin, H);
+                    else if (MODE == KDPT_REF_T2) traceRefWarp<true>(T, needTrav, w.r.o, w.r.d, w.tMin, H);
+                    else if (MODE == KDPT_BRUTE) traceBruteWarp<false>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.0001f, H);
+                    else traceBruteWarp<true>(T, needTrav, w.r.o, w.r.d, w.tMin, 0.0001f, H);
                     w.cp = make_float4(def[0][lane], def[1][lane], def[2][lane], def[3][lane]);
                     w.bm = make_int2(__float_as_int(def[4][lane]), __float_as_int(def[5][lane])); w.r.sdepth = def[6][lane];
                     w.hitGeom = __float_as_int(def[7][lane]);
@@ -1024,7 +1029,7 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
 {
     SceneView S{ctx->scene.geoms.as<kdpt_geom>(), ctx->scene.numGeoms, ctx->scene.geomBounds.as<float4>(), ctx->scene.materials.as<kdpt_material>(), ctx->scene.numMaterials};
     BounceArgs A; A.iter = bt.iterBase; A.depth = depth; A.stages = stages; A.softness = p.softness; A.enableSss = p.enableSss;
-    A.eps = (p.mode == KDPT_SHORTSTACK || p.mode == KDPT_REF_T2) ? 0.0001f : 0.00001f;
+    A.eps = (p.mode == KDPT_FULLSTACK || p.mode == KDPT_REF_T1) ? 0.00001f : 0.0001f;
     int grid = ctx->numSMs * 8;
     cudaStream_t s = ctx->stream;
     int* pc = p.compaction ? rb.packetCount : nullptr;
@@ -1060,7 +1065,9 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
     case KDPT_FULLSTACK: KDPT_LAUNCH_BOUNCE(KDPT_FULLSTACK); break;
     case KDPT_SHORTSTACK: KDPT_LAUNCH_BOUNCE(KDPT_SHORTSTACK); break;
     case KDPT_REF_T1: KDPT_LAUNCH_BOUNCE(KDPT_REF_T1); break;
-    default: KDPT_LAUNCH_BOUNCE(KDPT_REF_T2); break;
+    case KDPT_REF_T2: KDPT_LAUNCH_BOUNCE(KDPT_REF_T2); break;
+    case KDPT_BRUTE: KDPT_LAUNCH_BOUNCE(KDPT_BRUTE); break;
+    default: KDPT_LAUNCH_BOUNCE(KDPT_BRUTE_BBOX); break;
     }
 #undef KDPT_LAUNCH_BOUNCE
     launches++;
@@ -1268,7 +1275,8 @@ int kdpt_render(kdpt_ctx* ctx, int iter_begin, int iter_count, int iter_stride, 
         bt.iterStride = iter_stride; bt.npix = n;
         GenArgs gen; memset(&gen, 0, sizeof gen);
         gen.cam = ctx->scene.camera; gen.traceDepth = ctx->scene.traceDepth; gen.focal = p.focalLength;
-        for (int q = 0; q < B; q++) gen.ics.c[q] = makeIterConst(bt.iterBase + q * iter_stride, p);
+        // rayCaching: every iteration starts from iteration 1's camera rays (pathtrace.cu:2448-2456)
+        for (int q = 0; q < B; q++) { gen.ics.c[q] = makeIterConst(p.cacheRays ? 1 : bt.iterBase + q * iter_stride, p); gen.ics.c[q].iter = bt.iterBase + q * iter_stride; }
         if (maxBounces > 0) {
             beginBatchKernel<<<1, 64, 0, s>>>(rb.st, B, n);     // the first bounce kernel generates the camera rays itself
         } else {                                                // DEPTH <= 0: nothing is traced

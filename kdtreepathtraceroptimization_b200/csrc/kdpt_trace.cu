@@ -75,7 +75,9 @@ traceKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__
         if (MODE == KDPT_FULLSTACK) traceExactWarp<kMaxDepth, kCoopMin>(T, active, o, d, tin, 0.00001f, H);
         else if (MODE == KDPT_SHORTSTACK) traceExactWarp<4, kCoopMin>(T, active, o, d, tin, 0.0001f, H);
         else if (MODE == KDPT_REF_T1) traceRefWarp<false>(T, active, o, d, tin, H);
-        else traceRefWarp<true>(T, active, o, d, tin, H);
+        else if (MODE == KDPT_REF_T2) traceRefWarp<true>(T, active, o, d, tin, H);
+        else if (MODE == KDPT_BRUTE) traceBruteWarp<false>(T, active, o, d, tin, 0.0001f, H);
+        else traceBruteWarp<true>(T, active, o, d, tin, 0.0001f, H);
         if (active) {
             float4* out = reinterpret_cast<float4*>(hits + i);
             out[0] = make_float4(H.t, H.z, H.u, H.v);
@@ -269,6 +271,8 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
     case KDPT_SHORTSTACK: traceKernel<KDPT_SHORTSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_REF_T1: traceKernel<KDPT_REF_T1><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_REF_T2: traceKernel<KDPT_REF_T2><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
+    case KDPT_BRUTE: traceKernel<KDPT_BRUTE><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
+    case KDPT_BRUTE_BBOX: traceKernel<KDPT_BRUTE_BBOX><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     default: setError("kdpt_trace: unknown mode"); return KDPT_ERR_ARG;
     }
     KDPT_CUDA(cudaGetLastError());

@@ -18,8 +18,8 @@ static void usage()
             "usage: kdpt_render SCENE.txt [MESH.obj] [options]\n"
             "  --spp N            samples (default: ITERATIONS of the scene file)\n"
             "  --res WxH          override RES\n"
-            "  --mode M           ref_t2 (default, = SHORTSTACK on), ref_t1, shortstack, fullstack\n"
-            "  --no-aa  --dof-angle A  --focal F  --softness S  --sss  --no-compaction  --sort 0|1|2\n"
+            "  --mode M           ref_t2 (default, = SHORTSTACK on), ref_t1, shortstack, fullstack, brute (ENABLEKD off), brute_bbox (+ USEBBOX)\n"
+            "  --no-aa  --dof-angle A  --focal F  --softness S  --sss  --no-compaction  --sort 0|1|2  --cache-rays  --testing\n"
             "  --kd-depth D       KD build depth (default 13)   --synth-normals   --device N\n"
             "  --out FILE         .png (8-bit, like the reference's savePNG), .hdr (Radiance RGBE, its saveHDR), .pfm or .ppm\n"
             "  --cache-dir DIR    content-addressed binary cache of the loaded scene + KD tree (skips OBJ parse and build)\n"
@@ -157,9 +157,12 @@ int main(int argc, char** argv)
             std::string m = next();
             if (m == "ref_t2") p.mode = KDPT_REF_T2; else if (m == "ref_t1") p.mode = KDPT_REF_T1;
             else if (m == "shortstack") p.mode = KDPT_SHORTSTACK; else if (m == "fullstack") p.mode = KDPT_FULLSTACK;
+            else if (m == "brute") p.mode = KDPT_BRUTE; else if (m == "brute_bbox") p.mode = KDPT_BRUTE_BBOX;
             else { usage(); return 2; }
         }
         else if (a == "--no-aa") p.antialias = 0;
+        else if (a == "--cache-rays") p.cacheRays = 1;
+        else if (a == "--testing") p.testingmode = 1;
         else if (a == "--dof-angle") p.dofAngle = (float)atof(next());
         else if (a == "--focal") p.focalLength = (float)atof(next());
         else if (a == "--softness") p.softness = (float)atof(next());
@@ -257,10 +260,10 @@ int main(int argc, char** argv)
     }
     if (json)
         printf("{\"scene\": \"%s\", \"mesh\": \"%s\", \"resolution\": [%d, %d], \"spp\": %d, \"ray_bounces\": %llu, \"ms\": %.3f, "
-               "\"mrays_per_s\": %.2f, \"spp_per_s\": %.2f, \"launches\": %llu, \"cache_hit\": %d}\n",
+               "\"mrays_per_s\": %.2f, \"spp_per_s\": %.2f, \"launches\": %llu, \"cache_hit\": %d, \"intersect_ms_per_iteration\": %.4f}\n",
                sceneTxt.c_str(), obj.c_str(), W, H, spp, (unsigned long long)st.rayBounces, st.totalMs,
                st.totalMs > 0 ? st.rayBounces / (st.totalMs * 1e3) : 0.0, st.totalMs > 0 ? spp / (st.totalMs * 1e-3) : 0.0,
-               (unsigned long long)st.launches, cacheHit);
+               (unsigned long long)st.launches, cacheHit, spp > 0 ? st.intersectMs / spp : 0.0);
     kdpt_destroy(ctx);
     kdpt_scene_free(hs);
     return 0;

@@ -364,3 +364,27 @@ def test_compaction_and_sort_are_bit_exact(n):
             got = ctx.sort_paths(p)
             exp = p[np.argsort(p['materialIdHit'], kind='stable')]
             assert got.tobytes() == exp.tobytes(), (n, variant)
+
+
+def test_ray_cache_and_brute_force_modes(oracle):
+    """the two remaining switches of pathtrace(): rayCaching (pathtrace.cu:2448-2456 — every iteration starts from the camera
+    rays of iteration 1) against the oracle with the same switch, and the KD-less intersect modes (ENABLEKD off / USEBBOX),
+    whose images must be the bytes of the exact short-stack mode (same triangles, same nudge)"""
+    sc = _scene("cornell8_stanford_bunny.npz", 96, 96)
+    p = kdpt.default_params(mode=kdpt.SHORTSTACK, cacheRays=1)
+    with kdpt.Context(sc) as ctx:
+        ctx.clear_image(); st = ctx.render(1, 4, 1, p); cached = ctx.image()
+        ctx.clear_image(); ctx.render(1, 4, 1, kdpt.default_params(mode=kdpt.SHORTSTACK)); plain = ctx.image()
+        imgs = {}
+        for m in (kdpt.SHORTSTACK, kdpt.BRUTE, kdpt.BRUTE_BBOX):
+            ctx.clear_image(); ctx.render(1, 3, 1, kdpt.default_params(mode=m)); imgs[m] = ctx.image()
+    assert not np.array_equal(cached, plain)
+    oracle.lib.ko_set_ray_cache(1)
+    try:
+        o, total = _oracle_render(oracle, sc, p, [1, 2, 3, 4])
+    finally:
+        oracle.lib.ko_set_ray_cache(0)
+    assert abs(int(st['ray_bounces']) - int(total)) <= max(2, int(1e-3 * total))
+    assert (np.abs(cached - o).max(2) < 1e-3).mean() > 0.995
+    assert imgs[kdpt.BRUTE].tobytes() == imgs[kdpt.SHORTSTACK].tobytes()
+    assert imgs[kdpt.BRUTE_BBOX].tobytes() == imgs[kdpt.SHORTSTACK].tobytes()

@@ -34,6 +34,18 @@ def test_exact_modes_equal_brute_force_oracle(scene_ctx, oracle, mode, omode):
         assert (k['tri'] >= 0).sum() > 100
 
 
+@pytest.mark.parametrize("mode", [kdpt.BRUTE, kdpt.BRUTE_BBOX])
+def test_brute_force_modes_equal_the_brute_force_oracle(scene_ctx, oracle, mode):
+    """the reference's KD-less modes (pathTraceOneBounce, pathtrace.cu:402-628: every triangle for every ray, nudge 1e-4; with
+    the bounding-box reject of :497-511 in the second form)"""
+    g, ctx = scene_ctx
+    rays = g['rays'][:6000]
+    for tm in (None, g['t_min_in'][:6000]):
+        k = ctx.trace(rays, tm, mode)
+        assert_hits_equal(k, oracle.trace(KO_BRUTE_T2, g['nodes'], g['tris'], rays, tm, 6), g['tris'], f"mode {mode}")
+        assert k.tobytes() == ctx.trace(rays, tm, kdpt.SHORTSTACK).tobytes()
+
+
 @pytest.mark.parametrize("mode,omode,name", REF)
 def test_ref_modes_reproduce_the_reference_bit_for_bit(scene_ctx, oracle, mode, omode, name):
     g, ctx = scene_ctx
