@@ -86,7 +86,6 @@ struct LeanState {
     float tmin, tmax, t1, slack, zbound;
     unsigned cur;
     int sp, ringBase;
-    int li, le;         // leaf cursor: li < le = the lane is inside a leaf (next entry li), else at node `cur`
     bool dropped;
 };
 
@@ -94,7 +93,7 @@ struct LeanState {
 __device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinIn, LeanState& S, Hit& H)
 {
     initHit(H, tMinIn);
-    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = leanRoot(T); S.li = 0; S.le = 0;
+    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = leanRoot(T);
     if (T.numNodes == 0) return false;
     const float len = length(d);
     if (!(len > 0.0f) || !(len <= FLT_MAX)) return false;
@@ -143,7 +142,11 @@ __device__ __forceinline__ void leanTestTri(const Tree& T, const LeanState& S, H
 {
     const TriHot tr = loadTri(T, i);
     float u, v, z;
-    if (rayTriHit(S.o, S.d, tr.v0, tr.e1, tr.e2, u, v, z)) leanAccept(T, S, H, eps, i, tr.canon, u, v, z);
+    if (!rayTriHit(S.o, S.d, tr.v0, tr.e1, tr.e2, u, v, z)) return;
+    // a hit more than the exit slack (1e-3 world units) behind the best one cannot win on the nudged distance, which
+    // differs from |d| z by at most the nudge (1e-4): skip its normal fetch, normalisation and square roots
+    if (H.tri >= 0 && z > H.z + S.slack) return;
+    leanAccept(T, S, H, eps, i, tr.canon, u, v, z);
 }
 
 // a leaf the refinement could not split (>= 128 coincident triangles): all of it at once, through its chunk boxes.
@@ -173,77 +176,12 @@ static __device__ __noinline__ Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V
     return H;
 }
 
-#ifndef KDPT_LEAN_NODE_WEIGHT
-#define KDPT_LEAN_NODE_WEIGHT 1     // a round takes the leaf step when leafLanes * NODE_WEIGHT > nodeLanes * LEAF_WEIGHT
-#endif
-#ifndef KDPT_LEAN_LEAF_WEIGHT
-#define KDPT_LEAN_LEAF_WEIGHT 1
-#endif
-
-// One round of the warp (all 32 lanes call it; `alive` = the lane has a ray). Rays differ wildly in how many nodes
-// they cross between leaves and in how many triangles their leaves hold, so a "descend to the next leaf, then test the
-// leaf" step makes every lane wait for the longest descent and the fullest leaf of the warp (measured: 6 of 32 lanes
-// active per instruction). Here a round is ONE unit of work — one node step or one triangle test — and the warp takes
-// the kind more of its lanes are waiting for; the others keep their state and wait for a round of their kind.
-// Returns whether the lane still has a ray.
-template <bool RESTART>
-__device__ __forceinline__ bool leanRoundUnit(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
-                                          const uint4* sTop)
-{
-    const bool inLeaf = alive && S.li < S.le;
-    const unsigned leafMask = __ballot_sync(0xffffffffu, inLeaf);
-    const unsigned nodeMask = __ballot_sync(0xffffffffu, alive && !inLeaf);
-    if (__popc(leafMask) * KDPT_LEAN_NODE_WEIGHT > __popc(nodeMask) * KDPT_LEAN_LEAF_WEIGHT) {
-        if (inLeaf) {
-            leanTestTri(T, S, H, eps, S.li);
-            if (++S.li == S.le) alive = leanPop<RESTART>(T, S, H, sStack, lStack);
-        }
-        return alive;
-    }
-    if (alive && !inLeaf) {
-        const uint4 nd = leanNode(T, sTop, S.cur);
-        if ((nd.w & 3u) != kLeafFlag) {
-            const int a = (int)(nd.w & 3u);
-            const float split = __int_as_float((int)nd.x);
-            const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
-            const bool below = oa < split || (oa == split && da <= 0.0f);
-            const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
-            const float tp = (split - oa) * ia;
-            if (da == 0.0f || tp <= 0.0f || tp >= S.tmax) S.cur = nearc;
-            else if (tp <= S.tmin) S.cur = farc;
-            else {
-                const uint2 e = make_uint2(farc, __float_as_uint(S.tmax));
-                if (RESTART) {
-                    if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
-                    sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
-                } else {
-                    if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
-                    else lStack[S.sp - kLeanSmemStack] = e;
-                }
-                S.sp++;
-                S.cur = nearc; S.tmax = tp;
-            }
-        } else {
-            const int start = (int)nd.x, count = (int)nd.y;
-            if (count > 0 && nd.z == kNoChunks) { S.li = start; S.le = start + count; }
-            else {
-                if (count > 0) {
-                    const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
-                    H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
-                }
-                alive = leanPop<RESTART>(T, S, H, sStack, lStack);
-            }
-        }
-    }
-    return alive;
-}
-
-#ifndef KDPT_LEAN_TRI_UNROLL
-#define KDPT_LEAN_TRI_UNROLL 1      // triangles of a leaf tested per loop trip (their loads are issued together)
-#endif
-// "while-while" round: the lane descends to its next leaf, tests all of it, pops. The lanes of a warp wait for the longest
-// descent and the fullest leaf among them (measured on dragon_5: 6 of 32 lanes active per instruction), but a lane's own
-// instruction stream is minimal; this is the form that measured fastest (profiles/r2_lean_variants.txt).
+// One round of the warp's loop for a lane that has a ray ("while-while"): descend to the next leaf, test all of it, pop.
+// The lanes of a warp wait for the longest descent and the fullest leaf among them (measured on dragon_5: 6 of 32 lanes
+// active per instruction), but a lane's own instruction stream is minimal. Two forms that keep more lanes busy were built
+// and measured slower — one node step OR one triangle per round with the warp voting on the kind (10.7 lanes per
+// instruction, 2.8x the thread instructions), and rounds capped at 8 node steps + 8 triangles (no gain) — see
+// profiles/r2_lean_variants.txt (code: git history, commit "lean v3 (capped rounds) experiment").
 template <bool RESTART>
 __device__ __forceinline__ bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
                                               const uint4* sTop)
@@ -278,17 +216,7 @@ __device__ __forceinline__ bool leanRoundLeaf(const Tree& T, bool alive, LeanSta
     const int start = (int)nd.x, count = (int)nd.y;
     if (count > 0) {
         if (nd.z == kNoChunks) {
-            int i = start;
-            const int e = start + count;
-#if KDPT_LEAN_TRI_UNROLL >= 2
-            for (; i + 1 < e; i += 2) {
-                const TriHot ta = loadTri(T, i), tb = loadTri(T, i + 1);
-                float u, v, z;
-                if (rayTriHit(S.o, S.d, ta.v0, ta.e1, ta.e2, u, v, z)) leanAccept(T, S, H, eps, i, ta.canon, u, v, z);
-                if (rayTriHit(S.o, S.d, tb.v0, tb.e1, tb.e2, u, v, z)) leanAccept(T, S, H, eps, i + 1, tb.canon, u, v, z);
-            }
-#endif
-            for (; i < e; i++) leanTestTri(T, S, H, eps, i);
+            for (int i = start; i < start + count; i++) leanTestTri(T, S, H, eps, i);
         } else {
             const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
             H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
@@ -297,80 +225,11 @@ __device__ __forceinline__ bool leanRoundLeaf(const Tree& T, bool alive, LeanSta
     return leanPop<RESTART>(T, S, H, sStack, lStack);
 }
 
-#ifndef KDPT_LEAN_NODE_CAP
-#define KDPT_LEAN_NODE_CAP 8
-#endif
-#ifndef KDPT_LEAN_TRI_CAP
-#define KDPT_LEAN_TRI_CAP 8
-#endif
-// "capped while-while" round: as leanRoundLeaf, but a lane takes at most NODE_CAP node steps and then at most TRI_CAP
-// triangle tests per round and keeps its place (node, or cursor inside the leaf) for the next round. The first descent of a
-// ray crosses ~20 levels, later ones 2-5, and leaves hold 0 to dozens of entries: uncapped, every round lasts as long as
-// the warp's longest descent plus its fullest leaf while the average lane needs a third of either.
-template <bool RESTART>
-__device__ __forceinline__ bool leanRoundCapped(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
-                                                const uint4* sTop)
-{
-    if (!alive) return false;
-    if (S.li >= S.le) {
-        unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
-        uint4 nd = leanNode(T, sTop, cur);
-        int steps = KDPT_LEAN_NODE_CAP;
-        while ((nd.w & 3u) != kLeafFlag) {
-            if (steps-- == 0) { S.cur = cur; S.tmin = tmin; S.tmax = tmax; return true; }      // on with this descent next round
-            const int a = (int)(nd.w & 3u);
-            const float split = __int_as_float((int)nd.x);
-            const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
-            const bool below = oa < split || (oa == split && da <= 0.0f);
-            const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
-            const float tp = (split - oa) * ia;
-            if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
-            else if (tp <= tmin) cur = farc;
-            else {
-                const uint2 e = make_uint2(farc, __float_as_uint(tmax));
-                if (RESTART) {
-                    if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
-                    sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
-                } else {
-                    if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
-                    else lStack[S.sp - kLeanSmemStack] = e;
-                }
-                S.sp++;
-                cur = nearc; tmax = tp;
-            }
-            nd = leanNode(T, sTop, cur);
-        }
-        S.cur = cur; S.tmin = tmin; S.tmax = tmax;
-        const int start = (int)nd.x, count = (int)nd.y;
-        if (count > 0 && nd.z != kNoChunks) {
-            const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
-            H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
-            return leanPop<RESTART>(T, S, H, sStack, lStack);
-        }
-        if (count <= 0) return leanPop<RESTART>(T, S, H, sStack, lStack);
-        S.li = start; S.le = start + count;
-    }
-    const int e = S.le < S.li + KDPT_LEAN_TRI_CAP ? S.le : S.li + KDPT_LEAN_TRI_CAP;
-    for (int i = S.li; i < e; i++) leanTestTri(T, S, H, eps, i);
-    S.li = e;
-    if (e < S.le) return true;              // the rest of this leaf next round
-    return leanPop<RESTART>(T, S, H, sStack, lStack);
-}
-
-#ifndef KDPT_LEAN_V
-#define KDPT_LEAN_V 1       // 1: leanRoundLeaf (whole leaf per round), 2: leanRoundUnit (one node step or one triangle per round),
-#endif                      // 3: leanRoundCapped
 template <bool RESTART>
 __device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
                                           const uint4* sTop)
 {
-#if KDPT_LEAN_V == 2
-    return leanRoundUnit<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
-#elif KDPT_LEAN_V == 3
-    return leanRoundCapped<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
-#else
     return leanRoundLeaf<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
-#endif
 }
 
 } // namespace kdpt
