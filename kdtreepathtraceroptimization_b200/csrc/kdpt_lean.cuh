@@ -62,6 +62,33 @@ __device__ __forceinline__ uint4 leanNode(const Tree& T, const uint4* sTop, unsi
     return __ldg(T.nodes + cur);
 }
 
+// Bin key of a ray for leaf-ordered tracing: (the reference leaf in which the ray is when it is first inside the root
+// box, direction octant). Node IDs are DFS pre-order, so consecutive keys are neighbouring cells.
+__device__ __forceinline__ unsigned rayBinKey(const Tree& T, V3 o, V3 d)
+{
+    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float t0, t1;
+    unsigned node = 0;
+    if (T.numNodes > 0 && slab(o, inv, T.rootLo, T.rootHi, t0, t1)) {
+        // the point where the ray is when it is first inside the root box, then plain point location
+        const float te = t0 > 0.0f ? t0 : 0.0f;
+        const V3 p = mk(o.x + d.x * te, o.y + d.y * te, o.z + d.z * te);
+        // (down to the reference's leaf: in the refined view the nodes below it have indices >= numRefNodes)
+        for (int level = 0; level < kMaxDepth + 1; level++) {
+            const uint4 nd = __ldg(T.nodes + node);
+            const unsigned axis = nd.w & 3u;
+            if (axis == kLeafFlag) break;
+            const float split = __uint_as_float(nd.x);
+            const float pc = comp(p, (int)axis), dc = comp(d, (int)axis);
+            const bool left = pc < split || (pc == split && dc < 0.0f);
+            const unsigned child = left ? nd.z : nd.y;
+            if (child >= (unsigned)T.numRefNodes) break;
+            node = child;
+        }
+    }
+    return node * 8u + ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+}
+
 struct HitCand { float t, nx, ny, nz; int mtl; };
 // interpolated normal, nudged point and its distance (pathtrace.cu:993-998) of a triangle glm accepted: the rare part of
 // the leaf loop, kept out of line so that the loop itself stays small

@@ -50,6 +50,7 @@ struct IterConst {
 constexpr int kMaxBatch = KDPT_MAX_BATCH;   // iterations (samples) processed together by every launch
 constexpr int kSegShift = 26;               // the lane queue packs (segment, path index) in one word: <= 64 segments, < 2^26 paths each
 static_assert(kMaxBatch <= 64, "the lane queue packs the segment in 6 bits");
+constexpr int kQueueBinDefault = 0;         // leaf-ordered draining of the wavefront queue (see launchBounce)
 constexpr int kWavefrontMinTris = 0;         // refined leaf entries from which the bounce runs in its wavefront form
 constexpr int kTicketPackets = 1;       // 32-path packets a warp takes per ticket (amortises the atomic + segment lookup)
 
@@ -599,13 +600,64 @@ frontKernel(Tree T, SceneView S, PathSoA P, LoopState* st, BounceArgs A, Batch b
     bounceBody<MODE, GEN, true, true>(T, S, P, st, A, bt, accum, packetCount, packetAlive, nullptr, gen, sGeoms, sBounds, pk, nullptr, ng, gq);
 }
 
+// leaf-ordered draining of the queue (as kdpt_trace does for big batches): counting sort of the queued rays by
+// (reference leaf they start in, direction octant); the traversal kernel then takes its rays through order[]
+__global__ void __launch_bounds__(256)
+queueBinKeysKernel(Tree T, LoopState* st, int depth, RayQueue gq, unsigned* __restrict__ keys, unsigned* __restrict__ hist)
+{
+    const unsigned n = st->gqCount[depth];
+    const size_t cs = gq.cap;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* q = gq.work + i;
+        const unsigned key = rayBinKey(T, mk(q[0], q[cs], q[2 * cs]), mk(q[3 * cs], q[4 * cs], q[5 * cs]));
+        keys[i] = key;
+        atomicAdd(hist + key, 1u);
+    }
+}
+__global__ void __launch_bounds__(1024)
+queueBinScanKernel(unsigned* __restrict__ hist, int bins)
+{
+    __shared__ unsigned warpSums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < bins; base += 1024) {
+        const int k = base + threadIdx.x;
+        const unsigned v = k < bins ? hist[k] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = warpSums[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += t; }
+            warpSums[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        const unsigned excl = carry + warpSums[threadIdx.x >> 5] + incl - v;
+        if (k < bins) hist[k] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+queueBinScatterKernel(const unsigned* __restrict__ keys, LoopState* st, int depth, unsigned* __restrict__ offsets, unsigned* __restrict__ order)
+{
+    const unsigned n = st->gqCount[depth];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        order[atomicAdd(offsets + keys[i], 1u)] = i;
+}
+
 #ifndef KDPT_LEAN_MIN_BLOCKS
 #define KDPT_LEAN_MIN_BLOCKS 8
 #endif
 // the queued rays through the refined tree: kdpt_lean.cuh, rays and results in the queue's columns
 template <bool RESTART>
 __global__ void __launch_bounds__(kLeanThreads, KDPT_LEAN_MIN_BLOCKS)
-traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps)
+traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps, const unsigned* __restrict__ order)
 {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
@@ -632,8 +684,9 @@ traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps)
             base = __shfl_sync(FULL, base, 0);
             if (base + (unsigned)__popc(idle) >= n) more = false;
             if (!alive) {
-                const unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (i < n) {
+                    if (order) i = __ldg(order + i);
                     const float* q = gq.work + i;
                     const V3 o = mk(__ldg(q), __ldg(q + cs), __ldg(q + 2 * cs)), d = mk(__ldg(q + 3 * cs), __ldg(q + 4 * cs), __ldg(q + 5 * cs));
                     slot = i;
@@ -1043,15 +1096,42 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
         // wavefront form: front (phase A + the paths that miss the tree) -> lean traversal of the queued rays -> finish
         static const int envBlocks = getenv("KDPT_LEAN_BLOCKS") ? atoi(getenv("KDPT_LEAN_BLOCKS")) : KDPT_LEAN_MIN_BLOCKS;
         const int lgrid = ctx->numSMs * envBlocks;
+        // leaf-ordered draining (KDPT_QUEUE_BIN=0/1, development switch): only the later bounces are incoherent
+        static const int envBin = getenv("KDPT_QUEUE_BIN") ? atoi(getenv("KDPT_QUEUE_BIN")) : kQueueBinDefault;
+        const unsigned* order = nullptr;
+        if (envBin && depth > 0 && TV.numRefNodes > 1) {
+            const size_t slots = rb.gq.cap;
+            const int bins = TV.numRefNodes * 8;
+            int rc;
+            if ((rc = ctx->binTmp.ensure(sizeof(unsigned) * (2 * slots + (size_t)bins)))) return rc;
+            unsigned* keys = ctx->binTmp.as<unsigned>();
+            unsigned* ord = keys + slots;
+            unsigned* hist = ord + slots;
+            order = ord;
+            KDPT_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * (size_t)bins, s));
+        }
+        auto binQueue = [&]() {
+            if (!order) return;
+            const size_t slots = rb.gq.cap;
+            unsigned* keys = ctx->binTmp.as<unsigned>();
+            unsigned* ord = keys + slots;
+            unsigned* hist = ord + slots;
+            queueBinKeysKernel<<<grid, 256, 0, s>>>(TV, rb.st, depth, rb.gq, keys, hist);
+            queueBinScanKernel<<<1, 1024, 0, s>>>(hist, TV.numRefNodes * 8);
+            queueBinScatterKernel<<<grid, 256, 0, s>>>(keys, rb.st, depth, hist, ord);
+            launches += 3;
+        };
         if (p.mode == KDPT_FULLSTACK) {
             if (gen) frontKernel<KDPT_FULLSTACK, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, *gen, rb.gq);
             else frontKernel<KDPT_FULLSTACK, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, noGen, rb.gq);
-            traceQueueKernel<false><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps);
+            binQueue();
+            traceQueueKernel<false><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
             finishQueueKernel<KDPT_FULLSTACK><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, rb.gq);
         } else {
             if (gen) frontKernel<KDPT_SHORTSTACK, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, *gen, rb.gq);
             else frontKernel<KDPT_SHORTSTACK, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, noGen, rb.gq);
-            traceQueueKernel<true><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps);
+            binQueue();
+            traceQueueKernel<true><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
             finishQueueKernel<KDPT_SHORTSTACK><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, rb.gq);
         }
         launches += 3;

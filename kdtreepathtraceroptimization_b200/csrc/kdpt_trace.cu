@@ -155,27 +155,7 @@ binRaysKernel(Tree T, const kdpt_ray* __restrict__ rays, int n, unsigned* __rest
     if (i >= n) return;
     const float* r = reinterpret_cast<const float*>(rays + i);
     const V3 o = mk(__ldg(r + 0), __ldg(r + 1), __ldg(r + 2)), d = mk(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
-    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    float t0, t1;
-    unsigned node = 0;
-    if (T.numNodes > 0 && slab(o, inv, T.rootLo, T.rootHi, t0, t1)) {
-        // the point where the ray is when it is first inside the root box, then plain point location
-        const float te = t0 > 0.0f ? t0 : 0.0f;
-        const V3 p = mk(o.x + d.x * te, o.y + d.y * te, o.z + d.z * te);
-        // (down to the reference's leaf: in the refined view the nodes below it have indices >= numRefNodes)
-        for (int level = 0; level < kMaxDepth + 1; level++) {
-            const uint4 nd = __ldg(T.nodes + node);
-            const unsigned axis = nd.w & 3u;
-            if (axis == kLeafFlag) break;
-            const float split = __uint_as_float(nd.x);
-            const float pc = comp(p, (int)axis), dc = comp(d, (int)axis);
-            const bool left = pc < split || (pc == split && dc < 0.0f);
-            const unsigned child = left ? nd.z : nd.y;
-            if (child >= (unsigned)T.numRefNodes) break;
-            node = child;
-        }
-    }
-    const unsigned key = node * 8u + ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+    const unsigned key = rayBinKey(T, o, d);
     keys[i] = key;
     atomicAdd(hist + key, 1u);
 }
