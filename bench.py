@@ -91,7 +91,7 @@ def peak_l2():
         return None, "unmeasured"
 
 
-def roofline_object(workload, kernel, bytes_per_launch, launch_ms, working_set_bytes, extra):
+def roofline_object(workload, kernel, bytes_per_launch, launch_ms, working_set_bytes, extra, units_per_launch=None):
     """The contract's roofline object for the dominant kernel. `achieved` = algorithmic bytes of THIS design's traversal
     (profiles/algorithmic_bytes.json: node records, chunk boxes, triangles of the visited leaves, hit records, ray / path
     state — counted by running the product's own traversal functions on the host over the workload's rays) per launch
@@ -103,13 +103,15 @@ def roofline_object(workload, kernel, bytes_per_launch, launch_ms, working_set_b
     in_l2 = working_set_bytes <= L2_BYTES and l2 is not None
     peak = l2 if in_l2 else hbm
     tr = profile_json("r2_traffic.json").get(workload, {})
+    # ncu's DRAM bytes of the same kernels, per launch: the capture's bytes per ray(-bounce) x the rays of one of this run's launches
+    traffic = tr.get("dram_bytes_per_unit") * units_per_launch if (tr.get("dram_bytes_per_unit") and units_per_launch) else tr.get("dram_bytes_per_launch")
     roof = {"bound": "l2" if in_l2 else "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": tr.get("dram_bytes_per_launch"), "traffic_of": tr.get("kernel"), "kernel": kernel, "avg_launch_ms": launch_ms,
+            "traffic": traffic, "traffic_of": tr.get("kernel"), "kernel": kernel, "avg_launch_ms": launch_ms,
             "algorithmic_bytes_per_launch": bytes_per_launch, "working_set_bytes": int(working_set_bytes),
             "peak_source": l2_src if in_l2 else hbm_src, "frac_of_hbm": achieved / hbm, "frac_of_l2": (achieved / l2) if l2 else None,
             "hbm_peak_gbs": hbm, "l2_read_peak_gbs": l2,
             "ncu": {k: tr.get(k) for k in ("dram_gbs", "dram_frac_of_peak", "l2_gbs", "l2_frac_of_peak", "l1_hit_pct", "l2_hit_pct",
-                                           "issue_active_pct", "occupancy_pct", "lanes_per_instruction", "source") if k in tr}}
+                                           "issue_active_pct", "occupancy_pct", "lanes_per_instruction", "dram_bytes_per_unit", "source") if k in tr}}
     roof.update(extra)
     return roof
 
@@ -373,7 +375,7 @@ def run_trace_workload(args):
         ws = ctx.tree_info()["device_bytes"]
         roof = roofline_object(args.workload, "traceKernel<%s>" % (args.mode or "fullstack"), ab["bytes_per_ray_bounce"] * nrays, ms / K, ws,
                                {"algorithmic_bytes_per_ray": ab["bytes_per_ray_bounce"], "per_ray": {k: ab.get(k) for k in ("V", "B", "T", "H")},
-                                "unculled_reference_tree_bytes_per_ray": ab.get("unculled", {}).get("bytes_per_ray_bounce")})
+                                "unculled_reference_tree_bytes_per_ray": ab.get("unculled", {}).get("bytes_per_ray_bounce")}, units_per_launch=nrays)
         line = {"metric": "Mrays/s (traverse+intersect)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": desc, "rays_per_step_per_gpu": nrays, "tree": ctx.tree_info(), "tree_refined": ctx.refined_info(),
@@ -580,7 +582,8 @@ def main():
                                    {"kernel_share_of_step": st["intersect_ms"] / st["total_ms"],
                                     "algorithmic_bytes_per_ray_bounce": ab["bytes_per_ray_bounce"],
                                     "per_ray_bounce": {k: ab.get(k) for k in ("V", "B", "T", "H", "traversal_bytes", "path_bytes")},
-                                    "unculled_reference_tree_bytes_per_ray_bounce": ab.get("unculled", {}).get("bytes_per_ray_bounce")})
+                                    "unculled_reference_tree_bytes_per_ray_bounce": ab.get("unculled", {}).get("bytes_per_ray_bounce")},
+                                   units_per_launch=st["ray_bounces"] / nb)
         except Exception as e:      # never let the roofline bookkeeping kill the bench line
             roof = {"bound": "hbm", "achieved": None, "peak": peak_hbm()[0], "unit": "GB/s", "frac": None, "traffic": None, "error": repr(e)}
         # ---- what was rendered is checked: ray-bounces of iteration 1 against the oracle's count for this workload

@@ -18,6 +18,7 @@ constexpr int kCoopMin = KDPT_COOP_MIN;     // leaves with at least this many tr
 #endif
 constexpr int kBlockRange = KDPT_BLOCK_RANGE;   // packets per block-level ticket of a binned batch (see traceKernel)
 constexpr int kBinMinRays = 1 << 16;     // batches at least this big are traced in leaf order (see binRaysKernel)
+constexpr uint64_t kBinMinTreeBytes = 100ull << 20;
 
 // Persistent threads: a fixed grid (a multiple of the SM count) whose warps pull 32-ray packets from a global
 // counter until the batch is drained, so a warp stuck in a fat leaf does not hold back the rest of its block's
@@ -211,8 +212,11 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
     // three extra launches cost more than they save); KDPT_BIN_RAYS=0/1 forces it off/on in development
     static const int envBin = getenv("KDPT_BIN_RAYS") ? atoi(getenv("KDPT_BIN_RAYS")) : -1;
     const bool exact = mode == KDPT_FULLSTACK || mode == KDPT_SHORTSTACK;
-    const Tree& T = exact ? ctx->xtree : ctx->tree;
-    const bool bin = T.numRefNodes > 1 && (envBin >= 0 ? envBin != 0 : n >= kBinMinRays);
+    const Tree& T = ctx->tree;      // bin keys are reference leaves: the same in both views
+    // ... and when the tree is beyond the L2: on cache-resident trees the lean kernel does not need the coherence and the sort
+    // costs a quarter of the batch (dragon_5: 2043 Mrays/s unsorted, 1519 sorted; 10 M soup: 116 unsorted, 198 sorted)
+    const bool bigTree = ctx->deviceBytes >= kBinMinTreeBytes || !(exact && ctx->xNumNodes > 0);
+    const bool bin = T.numRefNodes > 1 && (envBin >= 0 ? envBin != 0 : (n >= kBinMinRays && bigTree));
     const unsigned* order = nullptr;
     if (bin) {
         const int bins = T.numRefNodes * 8;
@@ -236,7 +240,7 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
     if (grid > need) grid = need;
     // exact modes on a refined tree: the lean kernel (KDPT_LEAN=0 keeps the packet kernel, development switch)
     static const int envLean = getenv("KDPT_LEAN") ? atoi(getenv("KDPT_LEAN")) : 1;
-    if (exact && envLean && ctx->xtree.entryOf) {
+    if (exact && envLean && ctx->xNumNodes > 0) {
         static const int envBlocks = getenv("KDPT_LEAN_BLOCKS") ? atoi(getenv("KDPT_LEAN_BLOCKS")) : KDPT_LEAN_MIN_BLOCKS;
         int lgrid = ctx->numSMs * envBlocks;
         const int lneed = (n + kLeanThreads - 1) / kLeanThreads;
@@ -247,8 +251,8 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
         return KDPT_OK;
     }
     switch (mode) {
-    case KDPT_FULLSTACK: traceKernel<KDPT_FULLSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
-    case KDPT_SHORTSTACK: traceKernel<KDPT_SHORTSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
+    case KDPT_FULLSTACK: traceKernel<KDPT_FULLSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
+    case KDPT_SHORTSTACK: traceKernel<KDPT_SHORTSTACK><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_REF_T1: traceKernel<KDPT_REF_T1><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_REF_T2: traceKernel<KDPT_REF_T2><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
     case KDPT_BRUTE: traceKernel<KDPT_BRUTE><<<grid, kTraceThreads, 0, stream>>>(ctx->tree, dRays, dTmin, n, dHits, counter, order, blockTickets); break;
