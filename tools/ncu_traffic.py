@@ -17,7 +17,10 @@ idx = {h: i for i, h in enumerate(hdr)}
 def val(r, name, unit_scale=True):
     if name not in idx or r[idx[name]] in ("", "n/a"):
         return None
-    v = float(r[idx[name]].replace(",", ""))
+    try:
+        v = float(r[idx[name]].replace(",", ""))
+    except ValueError:          # "no data" on launches too short to sample
+        return None
     u = units[idx[name]]
     if unit_scale:
         scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1, "us": 1e-3, "ms": 1, "ns": 1e-6, "s": 1e3,
