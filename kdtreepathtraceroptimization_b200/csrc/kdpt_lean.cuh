@@ -210,7 +210,8 @@ static __device__ __noinline__ Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V
 // instruction, 2.8x the thread instructions), and rounds capped at 8 node steps + 8 triangles (no gain) — see
 // profiles/r2_lean_variants.txt (code: git history, commit "lean v3 (capped rounds) experiment"). A third, with the
 // triangle tests postponed into a per-warp shared-memory ring and run 32 wide, lost too (commit "queued triangle tests
-// experiment"): the lanes that walk on before their tests are done prune with a stale best hit.
+// experiment"): the lanes that walk on before their tests are done prune with a stale best hit; and the same dealing
+// without speculation (commit "dealt leaf tests experiment") costs in scans and shared-memory traffic what it returns.
 template <bool RESTART>
 __device__ __forceinline__ bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
                                               const uint4* sTop)
@@ -261,128 +262,5 @@ __device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& 
     return leanRoundLeaf<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
 }
 
-
-
-// ---- the warp's loop with the leaf tests of a round dealt evenly over the lanes -------------------------------------------
-// In a while-while round the triangle tests run with the few lanes whose leaf still has an entry at that loop trip
-// (measured: 5 of 32 at the top of the test, 1.2 in its division tail) and are a third of the kernel's instructions. Here the
-// lanes only DESCEND to their next leaf; the entries of all 32 leaves (<= kLeanDealPerLane each) are written as (lane, entry)
-// pairs to a per-warp array in shared memory and the warp tests them 32 at a time, each lane one pair with the owner's ray
-// read from shared memory; a glm hit is handed to its owner lane by shuffles and goes through the usual acceptance. Then
-// every lane pops. Same tests, same pruning, same hits as the while-while round — only who executes a test changes.
-constexpr int kLeanDealPerLane = 8;     // leaves with more entries (unsplittable ones) are tested by their lane on the spot
-struct LeanWarpShared {
-    unsigned ent[32 * kLeanDealPerLane];    // (owner lane << 27) | leaf entry
-    float ray[6][32];                       // o, d of every lane's current ray
-};
-
-template <bool RESTART, class Fetch, class Store>
-__device__ __forceinline__ void leanWarpLoopDealt(const Tree& T, float eps, unsigned n, unsigned* counter, Fetch fetch, Store store,
-                                                  uint2* sStack, uint2* lStack, const uint4* sTop, LeanWarpShared& W)
-{
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-    LeanState S; Hit H;
-    bool alive = false, more = n > 0;
-    unsigned slot = 0;
-    for (;;) {
-        const unsigned idle = __ballot_sync(FULL, !alive);
-        if (more && __popc(idle) >= KDPT_LEAN_REFILL_MIN) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(idle));
-            base = __shfl_sync(FULL, base, 0);
-            if (base + (unsigned)__popc(idle) >= n) more = false;
-            if (!alive) {
-                const unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-                if (i < n) {
-                    V3 o, d; float tin;
-                    slot = fetch(i, o, d, tin);
-                    alive = leanBegin(T, o, d, tin, S, H);
-                    if (alive) {
-                        W.ray[0][lane] = o.x; W.ray[1][lane] = o.y; W.ray[2][lane] = o.z;
-                        W.ray[3][lane] = d.x; W.ray[4][lane] = d.y; W.ray[5][lane] = d.z;
-                    } else store(slot, H);
-                }
-            }
-        }
-        if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
-        // ---- descend: every lane with a ray to its next leaf ----
-        int want = 0, estart = 0;
-        if (alive) {
-            unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
-            uint4 nd = leanNode(T, sTop, cur);
-            while ((nd.w & 3u) != kLeafFlag) {
-                const int a = (int)(nd.w & 3u);
-                const float split = __int_as_float((int)nd.x);
-                const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
-                const bool below = oa < split || (oa == split && da <= 0.0f);
-                const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
-                const float tp = (split - oa) * ia;
-                if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
-                else if (tp <= tmin) cur = farc;
-                else {
-                    const uint2 e = make_uint2(farc, __float_as_uint(tmax));
-                    if (RESTART) {
-                        if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
-                        sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
-                    } else {
-                        if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
-                        else lStack[S.sp - kLeanSmemStack] = e;
-                    }
-                    S.sp++;
-                    cur = nearc; tmax = tp;
-                }
-                nd = leanNode(T, sTop, cur);
-            }
-            S.tmax = tmax;
-            const int start = (int)nd.x, count = (int)nd.y;
-            if (count > 0) {
-                if (nd.z != kNoChunks) {
-                    const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
-                    H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
-                } else if (count > kLeanDealPerLane) {
-                    for (int i = start; i < start + count; i++) leanTestTri(T, S, H, eps, i);
-                } else { want = count; estart = start; }
-            }
-        }
-        // ---- deal: the round's (lane, entry) pairs, by an exclusive scan of the lanes' counts ----
-        unsigned incl = (unsigned)want;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const unsigned t = __shfl_up_sync(FULL, incl, off); if ((int)lane >= off) incl += t; }
-        const unsigned total = __shfl_sync(FULL, incl, 31);
-        {
-            const unsigned at = incl - (unsigned)want;
-            for (int k = 0; k < want; k++) W.ent[at + k] = (lane << 27) | (unsigned)(estart + k);
-        }
-        __syncwarp();
-        // ---- test 32 pairs at a time ----
-        for (unsigned q = 0; q < total; q += 32u) {
-            bool hit = false; unsigned owner = 0; int ti = 0, canon = 0; float u = 0.f, v = 0.f, z = 0.f;
-            if (q + lane < total) {
-                const unsigned e = W.ent[q + lane];
-                owner = e >> 27; ti = (int)(e & 0x7ffffffu);
-                const V3 O = mk(W.ray[0][owner], W.ray[1][owner], W.ray[2][owner]), D = mk(W.ray[3][owner], W.ray[4][owner], W.ray[5][owner]);
-                const TriHot tr = loadTri(T, ti);
-                canon = tr.canon;
-                hit = rayTriHit(O, D, tr.v0, tr.e1, tr.e2, u, v, z);
-            }
-            unsigned hm = __ballot_sync(FULL, hit);
-            while (hm) {        // a glm hit goes to its owner lane, which applies the acceptance rule to its own record
-                const int j = __ffs(hm) - 1;
-                hm &= hm - 1;
-                const unsigned ow = __shfl_sync(FULL, owner, j);
-                const int hi = __shfl_sync(FULL, ti, j), hc = __shfl_sync(FULL, canon, j);
-                const float hu = __shfl_sync(FULL, u, j), hv = __shfl_sync(FULL, v, j), hz = __shfl_sync(FULL, z, j);
-                if (lane == ow && !(H.tri >= 0 && hz > H.z + S.slack)) leanAccept(T, S, H, eps, hi, hc, hu, hv, hz);
-            }
-        }
-        __syncwarp();
-        // ---- pop ----
-        if (alive) {
-            alive = leanPop<RESTART>(T, S, H, sStack, lStack);
-            if (!alive) store(slot, H);
-        }
-    }
-}
 
 } // namespace kdpt

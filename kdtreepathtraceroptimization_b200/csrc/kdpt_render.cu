@@ -654,9 +654,6 @@ queueBinScatterKernel(const unsigned* __restrict__ keys, LoopState* st, int dept
 #ifndef KDPT_LEAN_MIN_BLOCKS
 #define KDPT_LEAN_MIN_BLOCKS 8
 #endif
-#ifndef KDPT_LEAN_DEALT
-#define KDPT_LEAN_DEALT 0       // 1: the leaf tests of a round dealt evenly over the lanes (leanWarpLoopDealt)
-#endif
 // the queued rays through the refined tree: kdpt_lean.cuh, rays and results in the queue's columns
 template <bool RESTART>
 __global__ void __launch_bounds__(kLeanThreads, KDPT_LEAN_MIN_BLOCKS)
@@ -671,23 +668,6 @@ traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps, const
     uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
     const unsigned n = st->gqCount[depth];
     const size_t cs = gq.cap;
-#if KDPT_LEAN_DEALT
-    __shared__ LeanWarpShared sW[kLeanThreads / 32];
-    auto fetch = [&](unsigned i, V3& o, V3& d, float& tin) -> unsigned {
-        if (order) i = __ldg(order + i);
-        const float* q = gq.work + i;
-        o = mk(__ldg(q), __ldg(q + cs), __ldg(q + 2 * cs)); d = mk(__ldg(q + 3 * cs), __ldg(q + 4 * cs), __ldg(q + 5 * cs));
-        tin = __ldg(q + 6 * cs);
-        return i;
-    };
-    auto storeHit = [&](unsigned i, const Hit& H) {
-        float* h = gq.hit + i;
-        h[0] = H.t; h[cs] = H.z; h[2 * cs] = __int_as_float(H.tri); h[3 * cs] = H.nx; h[4 * cs] = H.ny; h[5 * cs] = H.nz;
-        h[6 * cs] = __int_as_float(H.mtl);
-    };
-    (void)lane; (void)FULL;
-    leanWarpLoopDealt<RESTART>(T, eps, n, &st->gqTicket[depth], fetch, storeHit, sStack, lStack, sTop, sW[threadIdx.x >> 5]);
-#else
     LeanState S; Hit H;
     bool alive = false, more = n > 0;
     unsigned slot = 0;
@@ -720,7 +700,6 @@ traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps, const
         alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
         if (was && !alive) store(slot);
     }
-#endif
 }
 
 // phase C of the queued paths

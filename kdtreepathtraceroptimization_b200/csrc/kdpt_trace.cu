@@ -91,9 +91,6 @@ traceKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__
 #ifndef KDPT_LEAN_MIN_BLOCKS
 #define KDPT_LEAN_MIN_BLOCKS 8
 #endif
-#ifndef KDPT_LEAN_DEALT
-#define KDPT_LEAN_DEALT 0       // 1: the leaf tests of a round dealt evenly over the lanes (leanWarpLoopDealt)
-#endif
 template <bool RESTART>
 __global__ void __launch_bounds__(kLeanThreads, KDPT_LEAN_MIN_BLOCKS)
 traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__ tMinIn, int n, kdpt_hit* __restrict__ hits,
@@ -106,23 +103,6 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
     leanStageTop(T, sTop);
     uint2* sStack = sStackAll + threadIdx.x;
     uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
-#if KDPT_LEAN_DEALT
-    __shared__ LeanWarpShared sW[kLeanThreads / 32];
-    auto fetch = [&](unsigned i, V3& o, V3& d, float& tin) -> unsigned {
-        if (order) i = __ldg(order + i);
-        const float* r = reinterpret_cast<const float*>(rays + i);
-        o = mk(__ldg(r + 0), __ldg(r + 1), __ldg(r + 2)); d = mk(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
-        tin = tMinIn ? __ldg(tMinIn + i) : FLT_MAX;
-        return i;
-    };
-    auto storeHit = [&](unsigned i, const Hit& H) {
-        float4* out = reinterpret_cast<float4*>(hits + i);
-        out[0] = make_float4(H.t, H.z, H.u, H.v);
-        out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
-    };
-    (void)lane; (void)FULL;
-    leanWarpLoopDealt<RESTART>(T, eps, (unsigned)n, counter, fetch, storeHit, sStack, lStack, sTop, sW[threadIdx.x >> 5]);
-#else
     LeanState S; Hit H;
     bool alive = false, more = true;
     unsigned ray = 0;
@@ -160,7 +140,6 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
             out[1] = make_float4(__int_as_float(H.tri), H.nx, H.ny, H.nz);
         }
     }
-#endif
 }
 
 // ---- ray binning ------------------------------------------------------------------------------------------------
