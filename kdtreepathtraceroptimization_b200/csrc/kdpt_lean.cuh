@@ -31,6 +31,9 @@ namespace kdpt {
 constexpr int kLeanThreads = KDPT_LEAN_THREADS;
 constexpr int kLeanSmemStack = KDPT_LEAN_SMEM_STACK;
 constexpr int kLeanRing = 8;        // RESTART: entries in the ring
+// Shared-memory staging of the tree's top levels (north star / SURVEY §7 step 3): measured slower at 8, 10 and 11 levels
+// (-5 % / -16 % / -32 % on dragon1m, profiles/r2_lean_variants.txt — the top levels already hit L1 and the copy costs
+// residency), so it is not compiled in by default; -DKDPT_TOP_MAX_LEVELS=n with KDPT_TOP_LEVELS=n reproduces the sweep.
 #ifndef KDPT_TOP_MAX_LEVELS
 #define KDPT_TOP_MAX_LEVELS 0       // compile-time bound of the shared-memory copy of the tree's top levels (0: not compiled in)
 #endif
