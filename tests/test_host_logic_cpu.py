@@ -116,6 +116,20 @@ def test_flatten_rejects_malformed_trees(hostsim, golden_all):
     assert run(bad, g['tris']) == -1
     bad = g['nodes'].copy(); bad['parentID'][0] = 3
     assert run(bad, g['tris']) == -1
+    # a node listed as a child by two parents (a DAG: child-link paths longer than the parent-link depth the stacks are sized by)
+    bad = g['nodes'].copy()
+    inner = [i for i in range(len(bad)) if bad['leftID'][i] != -1]
+    a, b = inner[1], inner[2]
+    bad['leftID'][b] = bad['leftID'][a]
+    assert run(bad, g['tris']) == -1
+    # both children the same node
+    bad = g['nodes'].copy(); bad['rightID'][a] = bad['leftID'][a]
+    assert run(bad, g['tris']) == -1
+    # two leaves claiming overlapping triangle ranges
+    bad = g['nodes'].copy()
+    leaves = np.nonzero(bad['triIdSize'] > 1)[0]
+    bad['triIdStart'][leaves[1]] = bad['triIdStart'][leaves[0]] + 1
+    assert run(bad, g['tris']) == -1
 
 
 def test_c_abi_exports_every_declared_symbol():
