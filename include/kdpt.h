@@ -192,7 +192,10 @@ typedef struct {
                                    tested warp-cooperatively through chunk boxes); > 0: leaf size at which splitting stops */
     float refineTraversalCost;  /* <= 0: default (2.0); cost of one node step relative to one triangle test in the builder's
                                    surface-area heuristic */
-    int reserved[6];
+    int nodeForm;               /* how the exact modes' tree is laid out for their kernel. 0: default; 1: one 16-byte record per
+                                   node; 2: two levels per 32-byte record, small leaves named inline by their parents (half the
+                                   dependent loads of a descent) */
+    int reserved[5];
 } kdpt_build_opts;
 int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts* opts, kdpt_ctx** out);
 /* pathtraceFree */

@@ -66,7 +66,8 @@ class CParams(ctypes.Structure):
 
 
 class CBuildOpts(ctypes.Structure):
-    _fields_ = [("refineLeafMax", ctypes.c_int), ("refineTraversalCost", ctypes.c_float), ("reserved", ctypes.c_int * 6)]
+    _fields_ = [("refineLeafMax", ctypes.c_int), ("refineTraversalCost", ctypes.c_float), ("nodeForm", ctypes.c_int),
+                ("reserved", ctypes.c_int * 5)]
 
 
 class CRenderStats(ctypes.Structure):
@@ -267,8 +268,9 @@ def _ptr(a: np.ndarray):
 class Context:
     """kdpt_ctx: pathtraceInit on creation, pathtraceFree on close()."""
 
-    def __init__(self, scene: Scene, device: int = 0, refine_leaf_max: int = -1, refine_traversal_cost: float = 0.0):
-        """refine_leaf_max: kdpt_build_opts.refineLeafMax (-1 default, 0 = the exact modes walk the reference tree)"""
+    def __init__(self, scene: Scene, device: int = 0, refine_leaf_max: int = -1, refine_traversal_cost: float = 0.0, node_form: int = 0):
+        """refine_leaf_max: kdpt_build_opts.refineLeafMax (-1 default, 0 = the exact modes walk the reference tree);
+        node_form: kdpt_build_opts.nodeForm (0 default, 1 = 16-byte nodes, 2 = two-level records)"""
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         self.scene = scene
@@ -284,7 +286,7 @@ class Context:
         cs.objMaterialOffsets, cs.numShapes = _ptr(scene.offsets), len(scene.offsets)
         ctypes.memmove(ctypes.byref(cs.camera), scene.camera.ctypes.data, CAMERA.itemsize)
         cs.traceDepth = int(scene.trace_depth)
-        opts = CBuildOpts(int(refine_leaf_max), float(refine_traversal_cost))
+        opts = CBuildOpts(int(refine_leaf_max), float(refine_traversal_cost), int(node_form))
         _check(self._lib.kdpt_create_opts(ctypes.byref(cs), int(device), ctypes.byref(opts), ctypes.byref(self._h)), "kdpt_create_opts")
         self.device = device
 

@@ -145,6 +145,7 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
     if (bopts) {
         if (bopts->refineLeafMax >= 0) fopts.refineLeafMax = bopts->refineLeafMax;
         if (bopts->refineTraversalCost > 0.0f) fopts.traversalCost = bopts->refineTraversalCost;
+        if (bopts->nodeForm == 1 || bopts->nodeForm == 2) fopts.wideNodes = bopts->nodeForm == 2;
     }
     if (!flatten(scene->nodes, scene->numNodes, scene->tris, scene->numTris, flat, err, fopts)) { setError(err); return KDPT_ERR_ARG; }
     if (scene->numGeoms < 0 || scene->numMaterials < 0 || scene->numShapes < 0 ||
@@ -181,7 +182,7 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
     if ((rc = upload(ctx->treeMem[11], flat.chunkHi, (const HostF4**)&T.chunkHi, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[12], flat.superLo, (const HostF4**)&T.superLo, s))) return fail(rc);
     if ((rc = upload(ctx->treeMem[13], flat.superHi, (const HostF4**)&T.superHi, s))) return fail(rc);
-    T.entryOf = nullptr; T.top = nullptr; T.numTop = 0;
+    T.entryOf = nullptr; T.top = nullptr; T.numTop = 0; T.wide = nullptr; T.wideRoot = 0;
     T.numNodes = flat.numNodes; T.numTris = flat.numTris; T.numRefNodes = flat.numNodes;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = flat.rootLo[a]; T.rootHi[a] = flat.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = flat.tagCand[k];
@@ -207,6 +208,10 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
         if (!flat.xtop.empty()) {
             if ((rc = upload(ctx->treeMem[23], flat.xtop, (const HostNode**)&X.top, s))) return fail(rc);
             X.numTop = (int)flat.xtop.size();
+        }
+        if (!flat.xwide.empty()) {
+            if ((rc = upload(ctx->treeMem[24], flat.xwide, (const HostNode**)&X.wide, s))) return fail(rc);
+            X.wideRoot = flat.xwideRoot;
         }
         X.numNodes = (int)flat.xnodes.size(); X.numTris = flat.xNumTris;
         { size_t hot = (size_t)flat.xNumTris * 40; X.laneCost32 = hot > ((size_t)4 << 20) ? 192 : (hot > ((size_t)512 << 10) ? 64 : 32); }
@@ -261,7 +266,7 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
     flat.chunkLo.clear(); flat.chunkLo.shrink_to_fit(); flat.chunkHi.clear(); flat.chunkHi.shrink_to_fit();
     flat.superLo.clear(); flat.superLo.shrink_to_fit(); flat.superHi.clear(); flat.superHi.shrink_to_fit();
     ctx->xNumNodes = (int)flat.xnodes.size();
-    flat.xnodes.clear(); flat.xnodes.shrink_to_fit(); flat.xtriA.clear(); flat.xtriA.shrink_to_fit();
+    flat.xnodes.clear(); flat.xnodes.shrink_to_fit(); flat.xwide.clear(); flat.xwide.shrink_to_fit(); flat.xtriA.clear(); flat.xtriA.shrink_to_fit();
     flat.xtriB.clear(); flat.xtriB.shrink_to_fit(); flat.xtriC.clear(); flat.xtriC.shrink_to_fit();
     flat.xchunkLo.clear(); flat.xchunkLo.shrink_to_fit(); flat.xchunkHi.clear(); flat.xchunkHi.shrink_to_fit();
     flat.xsuperLo.clear(); flat.xsuperLo.shrink_to_fit(); flat.xsuperHi.clear(); flat.xsuperHi.shrink_to_fit();

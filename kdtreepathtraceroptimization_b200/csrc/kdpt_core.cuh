@@ -17,14 +17,19 @@
 
 #if defined(__CUDACC__)
 #define KDPT_HD __device__ __forceinline__
+#define KDPT_NOINLINE_FN static __device__ __noinline__
 #define KDPT_LDG(p) __ldg(p)
 #include <cuda_runtime.h>
 #else
 #define KDPT_HD inline
+#define KDPT_NOINLINE_FN static inline
 #define KDPT_LDG(p) (*(p))
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
+static inline float __uint_as_float(unsigned i) { float f; __builtin_memcpy(&f, &i, 4); return f; }
 static inline float __int_as_float(int i) { float f; __builtin_memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; __builtin_memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; __builtin_memcpy(&i, &f, 4); return i; }
@@ -76,6 +81,8 @@ struct Tree {
     const int* entryOf;      // refined view only (else NULL): TriBare index -> entry of nrmA/nrmB/nrmC (see below)
     const uint4* top;        // refined view only: breadth-first copy of the top levels for shared-memory staging (numTop nodes;
     int numTop;              // children inside the copy are named by position | 0x80000000), see kdpt_lean.cuh
+    const uint4* wide;       // refined view only (else NULL): the same tree, two levels per 32-byte record (kdpt_lean.cuh)
+    unsigned wideRoot;       // reference of the root in that form
     int numNodes;
     int numTris;
     int numRefNodes;         // nodes[i], i < numRefNodes, are the reference's nodes (both views)

@@ -19,7 +19,7 @@ uint64_t FlatTree::bytes() const
            (triA.size() + triB.size() + nrmA.size() + nrmB.size()) * sizeof(HostF4) +
            (triC.size() + nrmC.size()) * sizeof(HostF2) + triOrig.size() * sizeof(int) +
            (chunkLo.size() + chunkHi.size() + superLo.size() + superHi.size()) * sizeof(HostF4) +
-           xnodes.size() * sizeof(HostNode) + (xtriA.size() + xtriB.size()) * sizeof(HostF4) + xtriC.size() * sizeof(HostF2) +
+           (xnodes.size() + xwide.size()) * sizeof(HostNode) + (xtriA.size() + xtriB.size()) * sizeof(HostF4) + xtriC.size() * sizeof(HostF2) +
            (xchunkLo.size() + xchunkHi.size() + xsuperLo.size() + xsuperHi.size()) * sizeof(HostF4) + entryOf.size() * sizeof(int);
 }
 
@@ -324,11 +324,62 @@ void refineLeaves(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare
 }
 } // namespace
 
+// The refined tree, two levels per record (kdpt_lean.cuh: kWide*). A record is made for the root and for every interior
+// grandchild of a record's node, numbered in depth-first order (left subtrees first, like the nodes themselves); a leaf is
+// named by its parent: (first entry, count) inline when count <= 14 and the leaf has no chunk boxes, else the index of its
+// 16-byte leaf record in xnodes. Left empty if an index does not fit the 27 bits of a reference or the tree is too deep for
+// the kernels' stack (3 entries per record level).
+static void buildWide(FlatTree& out)
+{
+    const std::vector<HostNode>& N = out.xnodes;
+    out.xwide.clear(); out.xwideRoot = 0;
+    if (N.empty() || N.size() >= (1u << 27) || (size_t)out.xNumTris >= (1u << 27)) return;
+    auto isLeaf = [&](uint32_t id) { return (N[id].w & 3u) == 3u; };
+    auto leafRef = [&](uint32_t id) -> uint32_t {
+        const HostNode& h = N[id];
+        if (h.z == 0xffffffffu && h.y <= 14u) return 0x80000000u | (h.y << 27) | (h.y ? h.x : 0u);
+        return 0x80000000u | (15u << 27) | id;
+    };
+    if (isLeaf(0)) { out.xwideRoot = leafRef(0); out.xwide.assign(2, HostNode{0, 0, 0, 0}); return; }
+    // pass 1: number the records depth-first; pass 2: fill them
+    std::vector<uint32_t> recOf(N.size(), 0xffffffffu), order;
+    std::vector<uint32_t> stack{0u};
+    std::vector<int> level(N.size(), 0);
+    while (!stack.empty()) {
+        const uint32_t id = stack.back(); stack.pop_back();
+        if (level[id] >= 16) return;                        // kernels' stack: 3 entries per record level, kWideStack = 48
+        recOf[id] = (uint32_t)order.size(); order.push_back(id);
+        const uint32_t kids[2] = {N[id].z, N[id].y};        // left, right
+        uint32_t grand[4]; int ng = 0;
+        for (int k = 0; k < 2; k++)
+            if (!isLeaf(kids[k])) { grand[ng++] = N[kids[k]].z; grand[ng++] = N[kids[k]].y; }
+        for (int k = ng - 1; k >= 0; k--) if (!isLeaf(grand[k])) { level[grand[k]] = level[id] + 1; stack.push_back(grand[k]); }
+    }
+    auto ref = [&](uint32_t id) { return isLeaf(id) ? leafRef(id) : recOf[id]; };
+    out.xwide.resize(2 * order.size());
+    for (size_t r = 0; r < order.size(); r++) {
+        const HostNode& n = N[order[r]];
+        HostNode a{n.x, 0u, 0u, n.w & 3u}, b{0u, 0u, 0u, 0u};
+        const uint32_t kids[2] = {n.z, n.y};
+        for (int k = 0; k < 2; k++) {
+            const HostNode& c = N[kids[k]];
+            uint32_t axis = c.w & 3u, c0, c1 = 0u;
+            if (axis == 3u) c0 = leafRef(kids[k]);
+            else { c0 = ref(c.z); c1 = ref(c.y); (k == 0 ? a.y : a.z) = c.x; }
+            a.w |= axis << (2 + 2 * k);
+            if (k == 0) { b.x = c0; b.y = c1; } else { b.z = c0; b.w = c1; }
+        }
+        out.xwide[2 * r] = a; out.xwide[2 * r + 1] = b;
+    }
+    out.xwideRoot = 0;
+}
+
 FlattenOpts::FlattenOpts()
 {
     if (const char* e = getenv("KDPT_REFINE_LEAF")) refineLeafMax = atoi(e);
     if (const char* e = getenv("KDPT_REFINE_CT")) traversalCost = (float)atof(e);
     if (const char* e = getenv("KDPT_TOP_LEVELS")) topLevels = atoi(e);
+    if (const char* e = getenv("KDPT_WIDE")) wideNodes = atoi(e);
 }
 
 bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, FlatTree& out,
@@ -515,6 +566,7 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
         fillHot(xorder, tris, canon, nthreads, out.xtriA, out.xtriB, out.xtriC);
         out.entryOf.resize(numTris);
         parallelFor(numTris, nthreads, [&](int lo, int hi) { for (int i = lo; i < hi; i++) out.entryOf[order[i]] = i; });
+        if (opts.wideNodes) buildWide(out);
         if (opts.topLevels > 0) {
             // breadth-first copy of the first topLevels levels (at most 2^levels - 1 nodes)
             const int levels = opts.topLevels > 11 ? 11 : opts.topLevels;

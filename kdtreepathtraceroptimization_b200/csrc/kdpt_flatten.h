@@ -36,6 +36,10 @@ struct FlatTree {
     // the top levels of the refined tree in breadth-first order, for the kernels' shared-memory copy: same record, but a
     // child that is itself in this array is named by (its position | 0x80000000), any other child by its xnodes index
     std::vector<HostNode> xtop;
+    // the refined tree with two levels per record (FlattenOpts::wideNodes, layout and reference encoding: kdpt_lean.cuh): record k =
+    // xwide[2k], xwide[2k+1]; xwideRoot = reference of the root. Empty when the tree does not fit the encoding.
+    std::vector<HostNode> xwide;
+    uint32_t xwideRoot = 0;
     BulkVector<int> entryOf;                    // TriBare index -> entry of triA/.../nrmC holding it (inverse of triOrig)
     int xNumTris = 0, xMaxDepth = 0, xMaxLeaf = 0;
     float rootLo[3] = {0, 0, 0}, rootHi[3] = {0, 0, 0};
@@ -47,6 +51,7 @@ struct FlatTree {
 struct FlattenOpts {
     int refineLeafMax = 8;      // leaves with more triangles than this are split further for the exact modes; 0 = off
     float traversalCost = 2.0f; // SAH: cost of one node step relative to one triangle test
+    int wideNodes = 0;          // also emit the refined tree as two-level records with the small leaves named inline by their parents
     int topLevels = 0;          // levels of the refined tree copied breadth-first for shared-memory staging (0 = none, <= 11)
     FlattenOpts();              // defaults, overridable in development by KDPT_REFINE_LEAF / KDPT_REFINE_CT
 };

@@ -44,7 +44,7 @@ struct kdpt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     kdpt::Tree tree{};                 // device pointers: the reference view (reference-compatible modes)
     kdpt::Tree xtree{};                // the refined view (exact modes); equals `tree` when refinement is off
-    kdpt::DeviceBuffer treeMem[24];
+    kdpt::DeviceBuffer treeMem[25];
     kdpt::FlatTree info;               // host copy of the sizes only (vectors released after upload)
     uint64_t deviceBytes = 0;
     int xNumNodes = 0;                 // nodes of the refined view, 0 = refinement off

@@ -28,6 +28,9 @@ namespace kdpt {
 #define KDPT_LEAN_REFILL_MIN 8      // idle lanes needed before the warp fetches new rays (while rays are left): the fetch
                                     // code runs with only the idle lanes active (1 / 4 / 8: 1623 / 1695 / 1722 Mrays/s on dragon1m)
 #endif
+#ifndef KDPT_LEAN_SKIP_EMPTY
+#define KDPT_LEAN_SKIP_EMPTY 1      // empty leaves are popped inside the descent instead of ending the lane's round (see leanRoundLeaf)
+#endif
 constexpr int kLeanThreads = KDPT_LEAN_THREADS;
 constexpr int kLeanSmemStack = KDPT_LEAN_SMEM_STACK;
 constexpr int kLeanRing = 8;        // RESTART: entries in the ring
@@ -37,19 +40,30 @@ constexpr int kLeanRing = 8;        // RESTART: entries in the ring
 #ifndef KDPT_TOP_MAX_LEVELS
 #define KDPT_TOP_MAX_LEVELS 0       // compile-time bound of the shared-memory copy of the tree's top levels (0: not compiled in)
 #endif
+// Two levels per record (Tree::wide, built by kdpt_flatten.cpp:buildWide): a node with both children inlined,
+//   wide[2k]   = (split plane of the node, of its left child, of its right child, axis | left axis << 2 | right axis << 4)
+//   wide[2k+1] = (left child's left, left child's right, right child's left, right child's right)
+// where a child axis of 3 means "this child is a leaf" and its first slot names it. A reference is either a record index or
+//   kWideLeaf | count << 27 | first entry    (count <= 14: the leaf's range inline — no record to fetch, an empty leaf costs nothing)
+//   kWideLeaf | 15 << 27 | xnodes index      (chunked or bigger leaves: their 16-byte leaf record)
+// One fetch decides two levels, so a descent is half as many dependent loads; the far subtrees of both levels are cut by
+// their planes at once and go to the stack as up to three (reference, exit distance) entries, farthest first.
+constexpr unsigned kWideLeaf = 0x80000000u;
+constexpr unsigned kWideIndexMask = (1u << 27) - 1u;
+constexpr int kWideStack = 48;      // 3 entries per record level, at most 16 record levels (buildWide refuses deeper trees)
 constexpr int kTopMaxNodes = KDPT_TOP_MAX_LEVELS > 0 ? (1 << KDPT_TOP_MAX_LEVELS) - 1 : 1;
 constexpr unsigned kTopFlag = 0x80000000u;
 
 // the block's copy of the top levels (Tree::top); call from every thread of the block before the first round
-__device__ __forceinline__ void leanStageTop(const Tree& T, uint4* sTop)
+KDPT_HD void leanStageTop(const Tree& T, uint4* sTop)
 {
-#if KDPT_TOP_MAX_LEVELS > 0
+#if KDPT_TOP_MAX_LEVELS > 0 && defined(__CUDACC__)
     const int m = T.numTop < kTopMaxNodes ? T.numTop : 0;       // a copy that does not fit is not used at all
     for (int k = threadIdx.x; k < m; k += blockDim.x) sTop[k] = __ldg(T.top + k);
     __syncthreads();
 #endif
 }
-__device__ __forceinline__ unsigned leanRoot(const Tree& T)
+KDPT_HD unsigned leanRoot(const Tree& T)
 {
 #if KDPT_TOP_MAX_LEVELS > 0
     return (T.numTop > 0 && T.numTop < kTopMaxNodes) ? kTopFlag : 0u;
@@ -57,17 +71,17 @@ __device__ __forceinline__ unsigned leanRoot(const Tree& T)
     return 0u;
 #endif
 }
-__device__ __forceinline__ uint4 leanNode(const Tree& T, const uint4* sTop, unsigned cur)
+KDPT_HD uint4 leanNode(const Tree& T, const uint4* sTop, unsigned cur)
 {
 #if KDPT_TOP_MAX_LEVELS > 0
     if (cur & kTopFlag) return sTop[cur & ~kTopFlag];
 #endif
-    return __ldg(T.nodes + cur);
+    return KDPT_LDG(T.nodes + cur);
 }
 
 // Bin key of a ray for leaf-ordered tracing: (the reference leaf in which the ray is when it is first inside the root
 // box, direction octant). Node IDs are DFS pre-order, so consecutive keys are neighbouring cells.
-__device__ __forceinline__ unsigned rayBinKey(const Tree& T, V3 o, V3 d)
+KDPT_HD unsigned rayBinKey(const Tree& T, V3 o, V3 d)
 {
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     float t0, t1;
@@ -78,7 +92,7 @@ __device__ __forceinline__ unsigned rayBinKey(const Tree& T, V3 o, V3 d)
         const V3 p = mk(o.x + d.x * te, o.y + d.y * te, o.z + d.z * te);
         // (down to the reference's leaf: in the refined view the nodes below it have indices >= numRefNodes)
         for (int level = 0; level < kMaxDepth + 1; level++) {
-            const uint4 nd = __ldg(T.nodes + node);
+            const uint4 nd = KDPT_LDG(T.nodes + node);
             const unsigned axis = nd.w & 3u;
             if (axis == kLeafFlag) break;
             const float split = __uint_as_float(nd.x);
@@ -95,11 +109,11 @@ __device__ __forceinline__ unsigned rayBinKey(const Tree& T, V3 o, V3 d)
 struct HitCand { float t, nx, ny, nz; int mtl; };
 // interpolated normal, nudged point and its distance (pathtrace.cu:993-998) of a triangle glm accepted: the rare part of
 // the leaf loop, kept out of line so that the loop itself stays small
-static __device__ __noinline__ HitCand nudgedHit(const float4* __restrict__ nrmA, const float4* __restrict__ nrmB, const float2* __restrict__ nrmC,
+KDPT_NOINLINE_FN HitCand nudgedHit(const float4* __restrict__ nrmA, const float4* __restrict__ nrmB, const float2* __restrict__ nrmC,
                                           int i, float ox, float oy, float oz, float dx, float dy, float dz, float u, float v, float z, float eps)
 {
-    const float4 a = __ldg(nrmA + i), b = __ldg(nrmB + i);
-    const float2 c = __ldg(nrmC + i);
+    const float4 a = KDPT_LDG(nrmA + i), b = KDPT_LDG(nrmB + i);
+    const float2 c = KDPT_LDG(nrmC + i);
     const V3 o = mk(ox, oy, oz), d = mk(dx, dy, dz);
     const V3 n1 = mk(a.x, a.y, a.z), n2 = mk(a.w, b.x, b.y), n3 = mk(b.z, b.w, c.x);
     V3 hp = o + d * z;
@@ -120,10 +134,11 @@ struct LeanState {
 };
 
 // ray set-up shared by the kernels: false = the ray never enters the tree (H stays the "no hit" record)
-__device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinIn, LeanState& S, Hit& H)
+template <bool WIDE = false>
+KDPT_HD bool leanBegin(const Tree& T, V3 o, V3 d, float tMinIn, LeanState& S, Hit& H)
 {
     initHit(H, tMinIn);
-    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = leanRoot(T);
+    S.o = o; S.d = d; S.sp = 0; S.ringBase = 0; S.dropped = false; S.cur = WIDE ? T.wideRoot : leanRoot(T);
     if (T.numNodes == 0) return false;
     const float len = length(d);
     if (!(len > 0.0f) || !(len <= FLT_MAX)) return false;
@@ -138,8 +153,8 @@ __device__ __forceinline__ bool leanBegin(const Tree& T, V3 o, V3 d, float tMinI
 }
 
 // the leaf at hand is done: take the next pending subtree — it begins where this leaf's cell ends. false = ray finished.
-template <bool RESTART>
-__device__ __forceinline__ bool leanPop(const Tree& T, LeanState& S, const Hit& H, const uint2* sStack, const uint2* lStack)
+template <bool RESTART, bool WIDE = false>
+KDPT_HD bool leanPop(const Tree& T, LeanState& S, const Hit& H, const uint2* sStack, const uint2* lStack)
 {
     const float tmax = S.tmax;
     const float zb = (H.tri >= 0 ? fminf(H.z, S.zbound) : S.zbound) + S.slack;
@@ -153,22 +168,22 @@ __device__ __forceinline__ bool leanPop(const Tree& T, LeanState& S, const Hit& 
         return true;
     }
     if (RESTART && S.dropped && !(tmax >= S.t1 || tmax > zb)) {      // kd-restart: everything up to the exit of this leaf is done
-        S.cur = leanRoot(T); S.tmin = tmax; S.tmax = S.t1; S.ringBase = 0; S.dropped = false;
+        S.cur = WIDE ? T.wideRoot : leanRoot(T); S.tmin = tmax; S.tmax = S.t1; S.ringBase = 0; S.dropped = false;
         return true;
     }
     return false;
 }
 
 // glm accepted entry i (canonical index canon): nudged distance, then the reference's acceptance rule
-__device__ __forceinline__ void leanAccept(const Tree& T, const LeanState& S, Hit& H, float eps, int i, int canon, float u, float v, float z)
+KDPT_HD void leanAccept(const Tree& T, const LeanState& S, Hit& H, float eps, int i, int canon, float u, float v, float z)
 {
-    const int ni = T.entryOf ? __ldg(T.entryOf + canon) : i;
+    const int ni = T.entryOf ? KDPT_LDG(T.entryOf + canon) : i;
     const HitCand hc = nudgedHit(T.nrmA, T.nrmB, T.nrmC, ni, S.o.x, S.o.y, S.o.z, S.d.x, S.d.y, S.d.z, u, v, z, eps);
     if (hc.t > 0.0f && (H.t > hc.t || (H.t == hc.t && H.tri >= 0 && canon < H.tri))) {
         H.t = hc.t; H.z = z; H.u = u; H.v = v; H.tri = canon; H.nx = hc.nx; H.ny = hc.ny; H.nz = hc.nz; H.mtl = hc.mtl;
     }
 }
-__device__ __forceinline__ void leanTestTri(const Tree& T, const LeanState& S, Hit& H, float eps, int i)
+KDPT_HD void leanTestTri(const Tree& T, const LeanState& S, Hit& H, float eps, int i)
 {
     const TriHot tr = loadTri(T, i);
     float u, v, z;
@@ -186,7 +201,7 @@ struct LeanLeafRefs {
     const float2 *triC, *nrmC;
     const int* entryOf;
 };
-static __device__ __noinline__ Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V3 inv, float zbound, float slack, Hit H, float eps,
+KDPT_NOINLINE_FN Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V3 inv, float zbound, float slack, Hit H, float eps,
                                                    int start, int count, unsigned chunk0)
 {
     Tree T;
@@ -206,6 +221,38 @@ static __device__ __noinline__ Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V
     return H;
 }
 
+// one plane of a record against the interval [tmin, tmax] of the ray: which of the two sides first, where it ends, and
+// whether the other side follows (from there to tmax) — the near / far / both decision of the binary descent
+#ifdef KDPT_LEAN_COUNT
+static unsigned long long g_leanRounds, g_leanEmpty, g_leanTris, g_leanSteps;
+#endif
+struct PlaneCut { bool lowFirst, both; float tp; };
+KDPT_HD PlaneCut leanCut(const LeanState& S, int a, float split, float tmin, float tmax)
+{
+    const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+    const bool below = oa < split || (oa == split && da <= 0.0f);
+    const float tp = (split - oa) * ia;
+    const bool nearOnly = da == 0.0f || tp <= 0.0f || tp >= tmax;
+    const bool farOnly = !nearOnly && tp <= tmin;
+    PlaneCut c;
+    c.lowFirst = below != farOnly; c.both = !nearOnly && !farOnly; c.tp = tp;
+    return c;
+}
+
+template <bool RESTART, bool WIDE>
+KDPT_HD void leanPush(LeanState& S, uint2* sStack, uint2* lStack, unsigned node, float texit)
+{
+    const uint2 e = make_uint2(node, __float_as_uint(texit));
+    if (RESTART) {
+        if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
+        sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
+    } else {
+        if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
+        else lStack[S.sp - kLeanSmemStack] = e;
+    }
+    S.sp++;
+}
+
 // One round of the warp's loop for a lane that has a ray ("while-while"): descend to the next leaf, test all of it, pop.
 // The lanes of a warp wait for the longest descent and the fullest leaf among them (measured on dragon_5: 6 of 32 lanes
 // active per instruction), but a lane's own instruction stream is minimal. Two forms that keep more lanes busy were built
@@ -215,55 +262,95 @@ static __device__ __noinline__ Hit leanChunkedLeaf(LeanLeafRefs r, V3 o, V3 d, V
 // triangle tests postponed into a per-warp shared-memory ring and run 32 wide, lost too (commit "queued triangle tests
 // experiment"): the lanes that walk on before their tests are done prune with a stale best hit; and the same dealing
 // without speculation (commit "dealt leaf tests experiment") costs in scans and shared-memory traffic what it returns.
-template <bool RESTART>
-__device__ __forceinline__ bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
-                                              const uint4* sTop)
+template <bool RESTART, bool WIDE = false>
+KDPT_HD bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
+                           const uint4* sTop)
 {
     if (!alive) return false;
     unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
-    uint4 nd = leanNode(T, sTop, cur);
-    while ((nd.w & 3u) != kLeafFlag) {
-        const int a = (int)(nd.w & 3u);
-        const float split = __int_as_float((int)nd.x);
-        const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
-        const bool below = oa < split || (oa == split && da <= 0.0f);
-        const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
-        const float tp = (split - oa) * ia;
-        if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
-        else if (tp <= tmin) cur = farc;
-        else {
-            const uint2 e = make_uint2(farc, __float_as_uint(tmax));
-            if (RESTART) {
-                if (S.sp == kLeanRing) { S.ringBase = (S.ringBase + 1) & (kLeanRing - 1); S.sp--; S.dropped = true; }
-                sStack[((S.ringBase + S.sp) & (kLeanRing - 1)) * kLeanThreads] = e;
-            } else {
-                if (S.sp < kLeanSmemStack) sStack[S.sp * kLeanThreads] = e;
-                else lStack[S.sp - kLeanSmemStack] = e;
+    int start, count; unsigned chunk0 = kNoChunks;
+    // An EMPTY leaf (the surface-area heuristic cuts empty space off: two leaves of three a ray enters on dragon_5) is popped
+    // right here, inside the descent: the lane goes on to its next subtree instead of sitting out the other lanes' descents
+    // and triangle loops for nothing — a round ends at a leaf that has triangles, or with the ray.
+    for (;;) {
+    if (WIDE) {
+        while (!(cur & kWideLeaf)) {
+#ifdef KDPT_LEAN_COUNT
+            g_leanSteps++;
+#endif
+            const uint4 A = KDPT_LDG(T.wide + 2 * (size_t)cur), B = KDPT_LDG(T.wide + 2 * (size_t)cur + 1);
+            const PlaneCut c0 = leanCut(S, (int)(A.w & 3u), __uint_as_float(A.x), tmin, tmax);
+            // the child the ray is in first, over [tmin, e1]; the other one, if the ray reaches it, over [tp, tmax]
+            const float e1 = c0.both ? c0.tp : tmax;
+            const unsigned ax1 = c0.lowFirst ? (A.w >> 2) & 3u : (A.w >> 4) & 3u, ax2 = c0.lowFirst ? (A.w >> 4) & 3u : (A.w >> 2) & 3u;
+            const unsigned l1 = c0.lowFirst ? B.x : B.z, r1 = c0.lowFirst ? B.y : B.w;
+            const unsigned l2 = c0.lowFirst ? B.z : B.x, r2 = c0.lowFirst ? B.w : B.y;
+            const float s1 = __uint_as_float(c0.lowFirst ? A.y : A.z), s2 = __uint_as_float(c0.lowFirst ? A.z : A.y);
+            if (c0.both) {
+                if (ax2 == 3u) leanPush<RESTART, WIDE>(S, sStack, lStack, l2, tmax);
+                else {
+                    const PlaneCut c2 = leanCut(S, (int)ax2, s2, c0.tp, tmax);
+                    if (c2.both) leanPush<RESTART, WIDE>(S, sStack, lStack, c2.lowFirst ? r2 : l2, tmax);
+                    leanPush<RESTART, WIDE>(S, sStack, lStack, c2.lowFirst ? l2 : r2, c2.both ? c2.tp : tmax);
+                }
             }
-            S.sp++;
-            cur = nearc; tmax = tp;
+            if (ax1 == 3u) { cur = l1; tmax = e1; }
+            else {
+                const PlaneCut c1 = leanCut(S, (int)ax1, s1, tmin, e1);
+                if (c1.both) leanPush<RESTART, WIDE>(S, sStack, lStack, c1.lowFirst ? r1 : l1, e1);
+                cur = c1.lowFirst ? l1 : r1; tmax = c1.both ? c1.tp : e1;
+            }
         }
-        nd = leanNode(T, sTop, cur);
+        if (((cur >> 27) & 15u) == 15u) {
+            const uint4 nd = KDPT_LDG(T.nodes + (cur & kWideIndexMask));
+            start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
+        } else { start = (int)(cur & kWideIndexMask); count = (int)((cur >> 27) & 15u); }
+    } else {
+        uint4 nd = leanNode(T, sTop, cur);
+        while ((nd.w & 3u) != kLeafFlag) {
+#ifdef KDPT_LEAN_COUNT
+            g_leanSteps++;
+#endif
+            const int a = (int)(nd.w & 3u);
+            const float split = __int_as_float((int)nd.x);
+            const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+            const bool below = oa < split || (oa == split && da <= 0.0f);
+            const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+            const float tp = (split - oa) * ia;
+            if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
+            else if (tp <= tmin) cur = farc;
+            else { leanPush<RESTART, WIDE>(S, sStack, lStack, farc, tmax); cur = nearc; tmax = tp; }
+            nd = leanNode(T, sTop, cur);
+        }
+        start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
     }
     S.tmax = tmax;
-    const int start = (int)nd.x, count = (int)nd.y;
+#ifdef KDPT_LEAN_COUNT
+    if (count == 0) g_leanEmpty++;
+#endif
+    if (!KDPT_LEAN_SKIP_EMPTY || count > 0) break;
+    if (!leanPop<RESTART, WIDE>(T, S, H, sStack, lStack)) return false;
+    cur = S.cur; tmin = S.tmin; tmax = S.tmax;
+    }
+#ifdef KDPT_LEAN_COUNT
+    g_leanRounds++; g_leanTris += count;
+#endif
     if (count > 0) {
-        if (nd.z == kNoChunks) {
+        if (chunk0 == kNoChunks) {
             for (int i = start; i < start + count; i++) leanTestTri(T, S, H, eps, i);
         } else {
             const LeanLeafRefs r = {T.chunkLo, T.chunkHi, T.superLo, T.superHi, T.triA, T.triB, T.nrmA, T.nrmB, T.triC, T.nrmC, T.entryOf};
-            H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, nd.z);
+            H = leanChunkedLeaf(r, S.o, S.d, S.inv, S.zbound, S.slack, H, eps, start, count, chunk0);
         }
     }
-    return leanPop<RESTART>(T, S, H, sStack, lStack);
+    return leanPop<RESTART, WIDE>(T, S, H, sStack, lStack);
 }
 
-template <bool RESTART>
-__device__ __forceinline__ bool leanRound(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
-                                          const uint4* sTop)
+template <bool RESTART, bool WIDE = false>
+KDPT_HD bool leanRound(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
+                       const uint4* sTop)
 {
-    return leanRoundLeaf<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
+    return leanRoundLeaf<RESTART, WIDE>(T, alive, S, H, eps, sStack, lStack, sTop);
 }
-
 
 } // namespace kdpt

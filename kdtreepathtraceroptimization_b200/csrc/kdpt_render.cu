@@ -655,7 +655,7 @@ queueBinScatterKernel(const unsigned* __restrict__ keys, LoopState* st, int dept
 #define KDPT_LEAN_MIN_BLOCKS 8
 #endif
 // the queued rays through the refined tree: kdpt_lean.cuh, rays and results in the queue's columns
-template <bool RESTART>
+template <bool RESTART, bool WIDE>
 __global__ void __launch_bounds__(kLeanThreads, KDPT_LEAN_MIN_BLOCKS)
 traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps, const unsigned* __restrict__ order)
 {
@@ -665,7 +665,7 @@ traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps, const
     __shared__ uint4 sTop[kTopMaxNodes];
     leanStageTop(T, sTop);
     uint2* sStack = sStackAll + threadIdx.x;
-    uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
+    uint2 lStack[RESTART ? 1 : (WIDE ? kWideStack : kMaxDepth) - kLeanSmemStack];
     const unsigned n = st->gqCount[depth];
     const size_t cs = gq.cap;
     LeanState S; Hit H;
@@ -690,14 +690,14 @@ traceQueueKernel(Tree T, LoopState* st, int depth, RayQueue gq, float eps, const
                     const float* q = gq.work + i;
                     const V3 o = mk(__ldg(q), __ldg(q + cs), __ldg(q + 2 * cs)), d = mk(__ldg(q + 3 * cs), __ldg(q + 4 * cs), __ldg(q + 5 * cs));
                     slot = i;
-                    alive = leanBegin(T, o, d, __ldg(q + 6 * cs), S, H);
+                    alive = leanBegin<WIDE>(T, o, d, __ldg(q + 6 * cs), S, H);
                     if (!alive) store(i);
                 }
             }
         }
         if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
         const bool was = alive;
-        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
+        alive = leanRound<RESTART, WIDE>(T, alive, S, H, eps, sStack, lStack, sTop);
         if (was && !alive) store(slot);
     }
 }
@@ -1128,13 +1128,15 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
             if (gen) frontKernel<KDPT_FULLSTACK, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, *gen, rb.gq);
             else frontKernel<KDPT_FULLSTACK, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, noGen, rb.gq);
             binQueue();
-            traceQueueKernel<false><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
+            if (TV.wide) traceQueueKernel<false, true><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
+            else traceQueueKernel<false, false><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
             finishQueueKernel<KDPT_FULLSTACK><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, rb.gq);
         } else {
             if (gen) frontKernel<KDPT_SHORTSTACK, true><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, *gen, rb.gq);
             else frontKernel<KDPT_SHORTSTACK, false><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, noGen, rb.gq);
             binQueue();
-            traceQueueKernel<true><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
+            if (TV.wide) traceQueueKernel<true, true><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
+            else traceQueueKernel<true, false><<<lgrid, kLeanThreads, 0, s>>>(TV, rb.st, depth, rb.gq, A.eps, order);
             finishQueueKernel<KDPT_SHORTSTACK><<<grid, kThreads, 0, s>>>(TV, S, P, rb.st, A, bt, rb.accum, pc, pa, rb.gq);
         }
         launches += 3;

@@ -91,7 +91,7 @@ traceKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__
 #ifndef KDPT_LEAN_MIN_BLOCKS
 #define KDPT_LEAN_MIN_BLOCKS 8
 #endif
-template <bool RESTART>
+template <bool RESTART, bool WIDE>
 __global__ void __launch_bounds__(kLeanThreads, KDPT_LEAN_MIN_BLOCKS)
 traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restrict__ tMinIn, int n, kdpt_hit* __restrict__ hits,
                 unsigned* __restrict__ counter, const unsigned* __restrict__ order, float eps)
@@ -102,7 +102,7 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
     __shared__ uint4 sTop[kTopMaxNodes];
     leanStageTop(T, sTop);
     uint2* sStack = sStackAll + threadIdx.x;
-    uint2 lStack[RESTART ? 1 : kMaxDepth - kLeanSmemStack];
+    uint2 lStack[RESTART ? 1 : (WIDE ? kWideStack : kMaxDepth) - kLeanSmemStack];
     LeanState S; Hit H;
     bool alive = false, more = true;
     unsigned ray = 0;
@@ -122,7 +122,7 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
                     const V3 o = mk(__ldg(r + 0), __ldg(r + 1), __ldg(r + 2)), d = mk(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
                     const float tin = tMinIn ? __ldg(tMinIn + i) : FLT_MAX;
                     ray = i;
-                    alive = leanBegin(T, o, d, tin, S, H);
+                    alive = leanBegin<WIDE>(T, o, d, tin, S, H);
                     if (!alive) {       // never enters the tree
                         float4* out = reinterpret_cast<float4*>(hits + i);
                         out[0] = make_float4(H.t, H.z, H.u, H.v);
@@ -133,7 +133,7 @@ traceLeanKernel(Tree T, const kdpt_ray* __restrict__ rays, const float* __restri
         }
         if (!__any_sync(FULL, alive)) { if (!more) break; continue; }
         const bool was = alive;
-        alive = leanRound<RESTART>(T, alive, S, H, eps, sStack, lStack, sTop);
+        alive = leanRound<RESTART, WIDE>(T, alive, S, H, eps, sStack, lStack, sTop);
         if (was && !alive) {
             float4* out = reinterpret_cast<float4*>(hits + ray);
             out[0] = make_float4(H.t, H.z, H.u, H.v);
@@ -245,8 +245,14 @@ int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n,
         int lgrid = ctx->numSMs * envBlocks;
         const int lneed = (n + kLeanThreads - 1) / kLeanThreads;
         if (lgrid > lneed) lgrid = lneed;
-        if (mode == KDPT_FULLSTACK) traceLeanKernel<false><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.00001f);
-        else traceLeanKernel<true><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.0001f);
+        const bool wide = ctx->xtree.wide != nullptr;      // the tree as two-level records (kdpt_lean.cuh)
+        if (mode == KDPT_FULLSTACK) {
+            if (wide) traceLeanKernel<false, true><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.00001f);
+            else traceLeanKernel<false, false><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.00001f);
+        } else {
+            if (wide) traceLeanKernel<true, true><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.0001f);
+            else traceLeanKernel<true, false><<<lgrid, kLeanThreads, 0, stream>>>(ctx->xtree, dRays, dTmin, n, dHits, counter, order, 0.0001f);
+        }
         KDPT_CUDA(cudaGetLastError());
         return KDPT_OK;
     }

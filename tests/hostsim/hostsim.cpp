@@ -2,11 +2,25 @@
 // (csrc/kdpt_flatten.cpp) with g++ so the traversal LOGIC can be checked against the oracle on machines without a
 // GPU (pytest -m "not gpu"). It is never loaded by the package, bench.py or the C ABI; the product has no CPU path.
 #include "../../kdtreepathtraceroptimization_b200/csrc/kdpt_core.cuh"
+#include "../../kdtreepathtraceroptimization_b200/csrc/kdpt_lean.cuh"
 #include "../../kdtreepathtraceroptimization_b200/csrc/kdpt_flatten.h"
 #include <string>
 #include <string.h>
+#include <vector>
 
 using namespace kdpt;
+
+// the lean kernels' per-lane loop (kdpt_lean.cuh) for one ray: the same leanBegin / leanRound the kernels call, with the
+// "shared-memory" part of the stack in a host array of the same stride. steps = rounds (leaves visited).
+template <bool RESTART, bool WIDE>
+static void leanTraceOne(const Tree& X, V3 o, V3 d, float tin, float eps, Hit& H, unsigned long long* rounds)
+{
+    static thread_local std::vector<uint2> smem((size_t)(kLeanSmemStack > kLeanRing ? kLeanSmemStack : kLeanRing) * kLeanThreads);
+    uint2 lStack[kWideStack];
+    LeanState S;
+    bool alive = leanBegin<WIDE>(X, o, d, tin, S, H);
+    while (alive) { alive = leanRound<RESTART, WIDE>(X, alive, S, H, eps, smem.data() + 5, lStack, nullptr); if (rounds) ++*rounds; }
+}
 
 // refinement of the exact modes' tree: -1 = the product's default, 0 = off (walk the reference tree), n = leaf size
 static int g_refine = -1;
@@ -20,6 +34,7 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
     FlatTree F; std::string err;
     FlattenOpts fo;
     if (g_refine >= 0) fo.refineLeafMax = g_refine;
+    if (mode == 202 || mode == 203) fo.wideNodes = 1;
     if (!flatten(nodes, numNodes, tris, numTris, F, err, fo)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
     Tree T;
     T.nodes = (const uint4*)F.nodes.data();
@@ -28,7 +43,7 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
     T.nrmA = (const float4*)F.nrmA.data(); T.nrmB = (const float4*)F.nrmB.data(); T.nrmC = (const float2*)F.nrmC.data();
     T.triOrig = F.triOrig.data(); T.chunkLo = (const float4*)F.chunkLo.data(); T.chunkHi = (const float4*)F.chunkHi.data();
     T.superLo = (const float4*)F.superLo.data(); T.superHi = (const float4*)F.superHi.data();
-    T.entryOf = nullptr; T.top = nullptr; T.numTop = 0;
+    T.entryOf = nullptr; T.top = nullptr; T.numTop = 0; T.wide = nullptr; T.wideRoot = 0;
     T.numNodes = F.numNodes; T.numTris = F.numTris; T.numRefNodes = F.numNodes;
     for (int a = 0; a < 3; a++) { T.rootLo[a] = F.rootLo[a]; T.rootHi[a] = F.rootHi[a]; }
     for (int k = 0; k < 4; k++) T.tagCand[k] = F.tagCand[k];
@@ -41,7 +56,10 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
         X.superLo = (const float4*)F.xsuperLo.data(); X.superHi = (const float4*)F.xsuperHi.data();
         X.entryOf = F.entryOf.data();
         X.numNodes = (int)F.xnodes.size(); X.numTris = F.xNumTris;
+        if (!F.xwide.empty()) { X.wide = (const uint4*)F.xwide.data(); X.wideRoot = F.xwideRoot; }
     }
+    if (mode >= 200 && mode < 204 && F.xnodes.empty()) return -3;       // the lean loop walks the refined view only
+    if ((mode == 202 || mode == 203) && !X.wide) return -4;
     TraceCounters tc = {0, 0, 0, 0, 0};
     unsigned long long cn = 0, cl = 0, ct = 0, cb = 0, ch = 0;
     for (int i = 0; i < n; i++) {
@@ -54,6 +72,11 @@ extern "C" int hostsim_trace(const kdpt_node_bare* nodes, int numNodes, const kd
         case KDPT_FULLSTACK: traceExact<kMaxDepth, true>(X, o, d, tin, 0.00001f, H, &tc); break;
         case KDPT_SHORTSTACK: traceExact<4, true>(X, o, d, tin, 0.0001f, H, &tc); break;
         case 100: traceExact<1, true>(X, o, d, tin, 0.0001f, H, &tc); break; // restart stress: 1-entry stack
+        // the lean kernels' loop: 200 / 201 = full stack / ring + restart on 16-byte nodes, 202 / 203 = the same on two-level records
+        case 200: leanTraceOne<false, false>(X, o, d, tin, 0.00001f, H, &cl); break;
+        case 201: leanTraceOne<true, false>(X, o, d, tin, 0.0001f, H, &cl); break;
+        case 202: leanTraceOne<false, true>(X, o, d, tin, 0.00001f, H, &cl); break;
+        case 203: leanTraceOne<true, true>(X, o, d, tin, 0.0001f, H, &cl); break;
         case KDPT_REF_T1: traceRef<false>(T, o, d, tin, H, lastBary ? lastBary + 3 * i : nullptr); break;
         case KDPT_REF_T2: traceRef<true>(T, o, d, tin, H, lastBary ? lastBary + 3 * i : nullptr); break;
         default: return -2;
@@ -84,3 +107,12 @@ extern "C" int hostsim_canonical(const kdpt_node_bare* nodes, int numNodes, cons
     for (int i = 0; i < numTris; i++) { int c; memcpy(&c, &F.triC[i].y, 4); canonOut[F.triOrig[i]] = c; }
     return 0;
 }
+
+#ifdef HOSTSIM_COUNT
+// development: counters of the lean loop (rounds, rounds on an empty leaf, triangles, node steps); reset = 1 zeroes them
+extern "C" void hostsim_lean_counts(unsigned long long* c, int reset)
+{
+    if (reset) { g_leanRounds = g_leanEmpty = g_leanTris = g_leanSteps = 0; return; }
+    c[0] = g_leanRounds; c[1] = g_leanEmpty; c[2] = g_leanTris; c[3] = g_leanSteps;
+}
+#endif

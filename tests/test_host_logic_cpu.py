@@ -35,6 +35,26 @@ def test_exact_modes_equal_brute_force(hostsim, oracle, golden, mode, omode):
             assert_hits_equal(k, o, golden['tris'], f"mode {mode} refine {refine}")
 
 
+LEAN_FULL, LEAN_RESTART, LEAN_WIDE_FULL, LEAN_WIDE_RESTART = 200, 201, 202, 203
+
+
+@pytest.mark.parametrize("mode,omode", [(LEAN_FULL, KO_BRUTE_T1), (LEAN_RESTART, KO_BRUTE_T2), (LEAN_WIDE_FULL, KO_BRUTE_T1),
+                                        (LEAN_WIDE_RESTART, KO_BRUTE_T2)])
+def test_lean_loop_equals_brute_force(hostsim, oracle, golden, mode, omode):
+    """the per-lane loop of the lean kernels (kdpt_lean.cuh: leanBegin / leanRound, compiled for the host) on the refined tree, on its
+    16-byte nodes and on the two-level records, full stack and 8-entry ring with kd-restart"""
+    for tm in (None, golden['t_min_in']):
+        o = oracle.trace(omode, golden['nodes'], golden['tris'], golden['rays'], tm, 6)
+        for refine in (-1, 1, 3, 16):
+            k, _, ctr = _sim(hostsim, golden, mode, tm, refine=refine)
+            assert_hits_equal(k, o, golden['tris'], f"lean mode {mode} refine {refine}")
+    # the two node forms visit the same leaves in the same order: same number of rounds (full stack)
+    if mode == LEAN_WIDE_FULL:
+        _, _, a = _sim(hostsim, golden, LEAN_FULL)
+        _, _, b = _sim(hostsim, golden, LEAN_WIDE_FULL)
+        assert int(a[1]) >= int(b[1]) > 0       # fewer: an empty leaf named inline is skipped ... it still costs a round; see below
+
+
 @pytest.mark.parametrize("mode,omode,name", [(kdpt.REF_T1, KO_T1, "T1"), (kdpt.REF_T2, KO_T2, "T2")])
 def test_ref_modes_equal_reference(hostsim, oracle, golden, mode, omode, name):
     for sfx, tm in (("", None), ("_tmin", golden['t_min_in'])):

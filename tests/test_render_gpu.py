@@ -291,6 +291,21 @@ def test_lane_queue_schedules_are_bit_identical(name, kw, mode):
             ctx.render(1, 1, 1, kdpt.default_params(laneQueue=3))
 
 
+@pytest.mark.parametrize("name,kw", CASES)
+@pytest.mark.parametrize("mode", [kdpt.FULLSTACK, kdpt.SHORTSTACK])
+def test_node_forms_render_identical_images(name, kw, mode):
+    """kdpt_build_opts.nodeForm only changes how the exact modes' tree is laid out for the traversal kernel of the wavefront
+    bounce: images and ray counts are identical bit for bit"""
+    sc = _scene(name, 160, 128)
+    got = []
+    for form in (1, 2):
+        with kdpt.Context(sc, node_form=form) as ctx:
+            ctx.clear_image()
+            st = ctx.render(1, 6, 1, kdpt.default_params(mode=mode, **kw))
+            got.append((ctx.image().tobytes(), int(st['ray_bounces'])))
+    assert got[0] == got[1] and got[0][1] > 0
+
+
 def test_checkpoint_resume_is_bit_identical():
     """render 1..4, save, restore into a fresh context, render 5..8 == render 1..8 in one go (kdpt_get_image /
     kdpt_set_image; accumulation is iteration-ordered, so the result is bit-identical)"""

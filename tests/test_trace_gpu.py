@@ -34,6 +34,20 @@ def test_exact_modes_equal_brute_force_oracle(scene_ctx, oracle, mode, omode):
         assert (k['tri'] >= 0).sum() > 100
 
 
+@pytest.mark.parametrize("node_form", [1, 2])
+@pytest.mark.parametrize("mode,omode", EXACT)
+def test_both_node_forms_equal_brute_force_oracle(request, oracle, mode, omode, node_form):
+    """kdpt_build_opts.nodeForm: the exact modes' kernel on one 16-byte record per node and on two levels per 32-byte record
+    (small leaves named inline by their parents) — whichever is the default, both stay bit-exact"""
+    for f in SCENE_FILES:
+        path = os.path.join(GOLDEN, f)
+        g = np.load(path)
+        with kdpt.Context(kdpt.Scene.from_npz(path), node_form=node_form) as ctx:
+            for tm in (None, g['t_min_in']):
+                k = ctx.trace(g['rays'], tm, mode)
+                assert_hits_equal(k, oracle.trace(omode, g['nodes'], g['tris'], g['rays'], tm, 6), g['tris'], f"{f} mode {mode} form {node_form}")
+
+
 @pytest.mark.parametrize("mode", [kdpt.BRUTE, kdpt.BRUTE_BBOX])
 def test_brute_force_modes_equal_the_brute_force_oracle(scene_ctx, oracle, mode):
     """the reference's KD-less modes (pathTraceOneBounce, pathtrace.cu:402-628: every triangle for every ray, nudge 1e-4; with
@@ -143,6 +157,10 @@ def test_large_soup_properties(oracle):
         # the two exact modes carry the reference's two nudges (1e-5 / 1e-4), so they may legitimately disagree where
         # two surfaces are closer than that; anywhere else they must agree
         assert (a['tri'] != s['tri']).mean() < 1e-3
+        for form in (1, 2):         # both node forms of the exact modes' tree: the same bytes
+            with kdpt.Context(kdpt.Scene.tree_only(nodes, tris), node_form=form) as cf:
+                assert cf.trace(rays, None, kdpt.FULLSTACK).tobytes() == a.tobytes(), form
+                assert cf.trace(rays, None, kdpt.SHORTSTACK).tobytes() == s.tobytes(), form
         k = 4000
         assert_hits_equal(a[:k], oracle.trace(KO_BRUTE_T1, nodes, tris, rays[:k], None, 1), tris, "soup fullstack")
         assert_hits_equal(s[:k], oracle.trace(KO_BRUTE_T2, nodes, tris, rays[:k], None, 1), tris, "soup shortstack")
