@@ -92,7 +92,11 @@ typedef enum {
      * results as KDPT_SHORTSTACK; they exist for the reference's brute force / bounding box / kd-tree comparison */
     KDPT_BRUTE = 4,
     KDPT_BRUTE_BBOX = 5,
-    KDPT_MODE_COUNT = 6
+    /* the reference's view of the tree itself (VIZKD, key V; pathTraceOneBounceKDbareBoxes, pathtrace.cu:1738-1885): no
+     * triangles — every node box is drawn as a cube (boxIntersectionTestBox, intersections.h:51-104) of the LAST material,
+     * after the scene's own geoms. Render loop only (kdpt_render / kdpt_bounce); kdpt_trace refuses it */
+    KDPT_KDVIZ = 6,
+    KDPT_MODE_COUNT = 7
 } kdpt_mode;
 
 /* ---- render loop toggles: the trailing arguments of pathtrace(), src/pathtrace.h:8-21, defaults main.cpp:35-60 */

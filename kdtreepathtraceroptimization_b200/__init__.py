@@ -36,8 +36,8 @@ HIT = np.dtype([('t', 'f4'), ('z', 'f4'), ('u', 'f4'), ('v', 'f4'), ('tri', 'i4'
 assert (NODE.itemsize, TRI.itemsize, GEOM.itemsize, MATERIAL.itemsize, CAMERA.itemsize, RAY.itemsize, HIT.itemsize) == \
     (64, 76, 236, 56, 84, 24, 32)
 
-FULLSTACK, SHORTSTACK, REF_T1, REF_T2, BRUTE, BRUTE_BBOX = 0, 1, 2, 3, 4, 5
-MODES = {"fullstack": FULLSTACK, "shortstack": SHORTSTACK, "ref_t1": REF_T1, "ref_t2": REF_T2, "brute": BRUTE, "brute_bbox": BRUTE_BBOX}
+FULLSTACK, SHORTSTACK, REF_T1, REF_T2, BRUTE, BRUTE_BBOX, KDVIZ = 0, 1, 2, 3, 4, 5, 6
+MODES = {"fullstack": FULLSTACK, "shortstack": SHORTSTACK, "ref_t1": REF_T1, "ref_t2": REF_T2, "brute": BRUTE, "brute_bbox": BRUTE_BBOX, "kdviz": KDVIZ}
 
 
 class KdptError(RuntimeError):

@@ -124,6 +124,28 @@ int kdpt_destroy(kdpt_ctx* ctx)
     return KDPT_OK;
 }
 
+namespace kdpt {
+void geomWorldBounds(const float* m, float* lohi8)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+    for (int c = 0; c < 8; c++) {
+        double x = (c & 1) ? 0.5 : -0.5, y = (c & 2) ? 0.5 : -0.5, z = (c & 4) ? 0.5 : -0.5;
+        for (int a = 0; a < 3; a++) {
+            double v = (double)m[a] * x + (double)m[4 + a] * y + (double)m[8 + a] * z + (double)m[12 + a];
+            if (!(v == v) || !(fabs(v) < 1e30)) bad = true;
+            lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a];
+        }
+    }
+    for (int a = 0; a < 3; a++) {
+        double pad = 2e-3 + 1e-4 * (hi[a] - lo[a]) + 1e-5 * (fabs(lo[a]) > fabs(hi[a]) ? fabs(lo[a]) : fabs(hi[a]));
+        lohi8[a] = bad ? -INFINITY : (float)(lo[a] - pad);         // degenerate transform: never cull
+        lohi8[4 + a] = bad ? INFINITY : (float)(hi[a] + pad);
+    }
+    lohi8[3] = lohi8[7] = 0.f;
+}
+} // namespace kdpt
+
 int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out) { return kdpt_create_opts(scene, device, nullptr, out); }
 
 int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts* bopts, kdpt_ctx** out)
@@ -231,28 +253,14 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
         // sphere), padded: a ray that misses the padded box provably misses the geom, so the kernel can skip the exact
         // (and expensive) object-space test without changing any result. Two float4 per geom: (lo, -), (hi, -).
         std::vector<float> gb(8 * (size_t)(S.numGeoms > 0 ? S.numGeoms : 1), 0.f);
-        for (int g = 0; g < S.numGeoms; g++) {
-            const float* m = scene->geoms[g].transform;
-            double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-            bool bad = false;
-            for (int c = 0; c < 8; c++) {
-                double x = (c & 1) ? 0.5 : -0.5, y = (c & 2) ? 0.5 : -0.5, z = (c & 4) ? 0.5 : -0.5;
-                for (int a = 0; a < 3; a++) {
-                    double v = (double)m[a] * x + (double)m[4 + a] * y + (double)m[8 + a] * z + (double)m[12 + a];
-                    if (!(v == v) || !(fabs(v) < 1e30)) bad = true;
-                    lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a];
-                }
-            }
-            for (int a = 0; a < 3; a++) {
-                double pad = 2e-3 + 1e-4 * (hi[a] - lo[a]) + 1e-5 * (fabs(lo[a]) > fabs(hi[a]) ? fabs(lo[a]) : fabs(hi[a]));
-                gb[8 * g + a] = bad ? -INFINITY : (float)(lo[a] - pad);         // degenerate transform: never cull
-                gb[8 * g + 4 + a] = bad ? INFINITY : (float)(hi[a] + pad);
-            }
-        }
+        for (int g = 0; g < S.numGeoms; g++) geomWorldBounds(scene->geoms[g].transform, &gb[8 * (size_t)g]);
         if ((rc = S.geomBounds.alloc(sizeof(float) * gb.size()))) return fail(rc);
         if ((e = cudaMemcpyAsync(S.geomBounds.p, gb.data(), sizeof(float) * gb.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(cudaFail(e, "upload geom bounds"));
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(cudaFail(e, "cudaStreamSynchronize"));
     }
+    ctx->nodeBoxes.resize(6 * (size_t)scene->numNodes);
+    for (int i = 0; i < scene->numNodes; i++)
+        for (int a = 0; a < 3; a++) { ctx->nodeBoxes[6 * (size_t)i + a] = scene->nodes[i].mins[a]; ctx->nodeBoxes[6 * (size_t)i + 3 + a] = scene->nodes[i].maxs[a]; }
     S.camera = scene->camera; S.traceDepth = scene->traceDepth;
     S.hasCamera = scene->camera.resolution[0] > 0 && scene->camera.resolution[1] > 0;
     if ((rc = ctx->counter.alloc(256))) return fail(rc);

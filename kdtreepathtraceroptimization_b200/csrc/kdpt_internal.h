@@ -49,6 +49,11 @@ struct kdpt_ctx {
     uint64_t deviceBytes = 0;
     int xNumNodes = 0;                 // nodes of the refined view, 0 = refinement off
     kdpt::SceneDev scene;
+    // KDPT_KDVIZ: the node boxes (mins, maxs: 6 floats per reference node) and, from the first render in that mode on, the
+    // scene's geoms followed by one cube geom per node, with their padded world boxes
+    std::vector<float> nodeBoxes;
+    kdpt::DeviceBuffer vizGeoms, vizBounds;
+    int vizCount = 0;
     // traversal scratch
     kdpt::DeviceBuffer rays, tmin, hits, counter, binTmp;
     // render loop state
@@ -68,6 +73,11 @@ namespace kdpt {
 // soup, 16.7 M rays from pinned host buffers, end to end: on a box with fast host copies (~25 GB/s) 2 M-ray slices 66.6
 // Mrays/s, 4 M 83.6, unsliced 84-92; on a box with slow ones (~6.5 GB/s) unsliced drops to 57. 4 M is the robust choice.
 constexpr int kTraceSlice = 1 << 22;
+// kdpt_scene.cpp — the cube geom boxIntersectionTestBox (intersections.h:51-66) makes of a box: scale = extent, translation =
+// centre, matrices as glm builds them (KDPT_KDVIZ)
+void nodeBoxGeom(const float* mins, const float* maxs, int materialid, kdpt_geom* out);
+// kdpt_api.cu — padded world-space AABB of the unit cube under a geom's transform: (lo, -), (hi, -), 8 floats
+void geomWorldBounds(const float* transform, float* lohi8);
 // kdpt_trace.cu
 int launchTrace(kdpt_ctx* ctx, const kdpt_ray* dRays, const float* dTmin, int n, kdpt_hit* dHits, int mode,
                 cudaStream_t stream);

@@ -29,7 +29,10 @@ namespace kdpt {
                                     // code runs with only the idle lanes active (1 / 4 / 8: 1623 / 1695 / 1722 Mrays/s on dragon1m)
 #endif
 #ifndef KDPT_LEAN_SKIP_EMPTY
-#define KDPT_LEAN_SKIP_EMPTY 1      // empty leaves are popped inside the descent instead of ending the lane's round (see leanRoundLeaf)
+#define KDPT_LEAN_SKIP_EMPTY 0      // what a lane does at an empty leaf: 0 end the round, 1 / 2 pop inside the descent (see leanRoundLeaf)
+#endif
+#ifndef KDPT_LEAN_TRIP_CAP
+#define KDPT_LEAN_TRIP_CAP 0        // KDPT_LEAN_SKIP_EMPTY == 2: a round also ends after this many loop trips without a leaf (0: no cap)
 #endif
 constexpr int kLeanThreads = KDPT_LEAN_THREADS;
 constexpr int kLeanSmemStack = KDPT_LEAN_SMEM_STACK;
@@ -253,6 +256,57 @@ KDPT_HD void leanPush(LeanState& S, uint2* sStack, uint2* lStack, unsigned node,
     S.sp++;
 }
 
+// one step of the descent on a two-level record: cur becomes the first of the (up to four) grandchildren the ray visits, the
+// others go to the stack farthest first
+template <bool RESTART>
+KDPT_HD void leanWideStep(const Tree& T, LeanState& S, uint2* sStack, uint2* lStack, unsigned& cur, float tmin, float& tmax)
+{
+    const uint4 A = KDPT_LDG(T.wide + 2 * (size_t)cur), B = KDPT_LDG(T.wide + 2 * (size_t)cur + 1);
+    const PlaneCut c0 = leanCut(S, (int)(A.w & 3u), __uint_as_float(A.x), tmin, tmax);
+    // the child the ray is in first, over [tmin, e1]; the other one, if the ray reaches it, over [tp, tmax]
+    const float e1 = c0.both ? c0.tp : tmax;
+    const unsigned ax1 = c0.lowFirst ? (A.w >> 2) & 3u : (A.w >> 4) & 3u, ax2 = c0.lowFirst ? (A.w >> 4) & 3u : (A.w >> 2) & 3u;
+    const unsigned l1 = c0.lowFirst ? B.x : B.z, r1 = c0.lowFirst ? B.y : B.w;
+    const unsigned l2 = c0.lowFirst ? B.z : B.x, r2 = c0.lowFirst ? B.w : B.y;
+    const float s1 = __uint_as_float(c0.lowFirst ? A.y : A.z), s2 = __uint_as_float(c0.lowFirst ? A.z : A.y);
+    if (c0.both) {
+        if (ax2 == 3u) leanPush<RESTART, true>(S, sStack, lStack, l2, tmax);
+        else {
+            const PlaneCut c2 = leanCut(S, (int)ax2, s2, c0.tp, tmax);
+            if (c2.both) leanPush<RESTART, true>(S, sStack, lStack, c2.lowFirst ? r2 : l2, tmax);
+            leanPush<RESTART, true>(S, sStack, lStack, c2.lowFirst ? l2 : r2, c2.both ? c2.tp : tmax);
+        }
+    }
+    if (ax1 == 3u) { cur = l1; tmax = e1; }
+    else {
+        const PlaneCut c1 = leanCut(S, (int)ax1, s1, tmin, e1);
+        if (c1.both) leanPush<RESTART, true>(S, sStack, lStack, c1.lowFirst ? r1 : l1, e1);
+        cur = c1.lowFirst ? l1 : r1; tmax = c1.both ? c1.tp : e1;
+    }
+}
+// a leaf reference of that form: its range, inline or from its 16-byte record
+KDPT_HD void leanWideLeaf(const Tree& T, unsigned cur, int& start, int& count, unsigned& chunk0)
+{
+    if (((cur >> 27) & 15u) == 15u) {
+        const uint4 nd = KDPT_LDG(T.nodes + (cur & kWideIndexMask));
+        start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
+    } else { start = (int)(cur & kWideIndexMask); count = (int)((cur >> 27) & 15u); chunk0 = kNoChunks; }
+}
+// one step of the descent on a 16-byte interior node
+template <bool RESTART>
+KDPT_HD void leanStep(const uint4 nd, LeanState& S, uint2* sStack, uint2* lStack, unsigned& cur, float tmin, float& tmax)
+{
+    const int a = (int)(nd.w & 3u);
+    const float split = __int_as_float((int)nd.x);
+    const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+    const bool below = oa < split || (oa == split && da <= 0.0f);
+    const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
+    const float tp = (split - oa) * ia;
+    if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
+    else if (tp <= tmin) cur = farc;
+    else { leanPush<RESTART, false>(S, sStack, lStack, farc, tmax); cur = nearc; tmax = tp; }
+}
+
 // One round of the warp's loop for a lane that has a ray ("while-while"): descend to the next leaf, test all of it, pop.
 // The lanes of a warp wait for the longest descent and the fullest leaf among them (measured on dragon_5: 6 of 32 lanes
 // active per instruction), but a lane's own instruction stream is minimal. Two forms that keep more lanes busy were built
@@ -262,6 +316,11 @@ KDPT_HD void leanPush(LeanState& S, uint2* sStack, uint2* lStack, unsigned node,
 // triangle tests postponed into a per-warp shared-memory ring and run 32 wide, lost too (commit "queued triangle tests
 // experiment"): the lanes that walk on before their tests are done prune with a stale best hit; and the same dealing
 // without speculation (commit "dealt leaf tests experiment") costs in scans and shared-memory traffic what it returns.
+//
+// KDPT_LEAN_SKIP_EMPTY: what a lane does at an EMPTY leaf (the surface-area heuristic cuts empty space off: two leaves of
+// three a ray enters on dragon_5 are empty). 0: the round ends there like at any leaf. 1: it pops and descends again before
+// the warp moves on to the triangles (descent loop nested in a pop loop). 2: the same in ONE loop whose trips are either a
+// node step or a pop, so that a lane never waits for the other lanes' descents before it pops.
 template <bool RESTART, bool WIDE = false>
 KDPT_HD bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
                            const uint4* sTop)
@@ -269,69 +328,71 @@ KDPT_HD bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, floa
     if (!alive) return false;
     unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
     int start, count; unsigned chunk0 = kNoChunks;
-    // An EMPTY leaf (the surface-area heuristic cuts empty space off: two leaves of three a ray enters on dragon_5) is popped
-    // right here, inside the descent: the lane goes on to its next subtree instead of sitting out the other lanes' descents
-    // and triangle loops for nothing — a round ends at a leaf that has triangles, or with the ray.
-    for (;;) {
-    if (WIDE) {
-        while (!(cur & kWideLeaf)) {
-#ifdef KDPT_LEAN_COUNT
-            g_leanSteps++;
-#endif
-            const uint4 A = KDPT_LDG(T.wide + 2 * (size_t)cur), B = KDPT_LDG(T.wide + 2 * (size_t)cur + 1);
-            const PlaneCut c0 = leanCut(S, (int)(A.w & 3u), __uint_as_float(A.x), tmin, tmax);
-            // the child the ray is in first, over [tmin, e1]; the other one, if the ray reaches it, over [tp, tmax]
-            const float e1 = c0.both ? c0.tp : tmax;
-            const unsigned ax1 = c0.lowFirst ? (A.w >> 2) & 3u : (A.w >> 4) & 3u, ax2 = c0.lowFirst ? (A.w >> 4) & 3u : (A.w >> 2) & 3u;
-            const unsigned l1 = c0.lowFirst ? B.x : B.z, r1 = c0.lowFirst ? B.y : B.w;
-            const unsigned l2 = c0.lowFirst ? B.z : B.x, r2 = c0.lowFirst ? B.w : B.y;
-            const float s1 = __uint_as_float(c0.lowFirst ? A.y : A.z), s2 = __uint_as_float(c0.lowFirst ? A.z : A.y);
-            if (c0.both) {
-                if (ax2 == 3u) leanPush<RESTART, WIDE>(S, sStack, lStack, l2, tmax);
-                else {
-                    const PlaneCut c2 = leanCut(S, (int)ax2, s2, c0.tp, tmax);
-                    if (c2.both) leanPush<RESTART, WIDE>(S, sStack, lStack, c2.lowFirst ? r2 : l2, tmax);
-                    leanPush<RESTART, WIDE>(S, sStack, lStack, c2.lowFirst ? l2 : r2, c2.both ? c2.tp : tmax);
-                }
-            }
-            if (ax1 == 3u) { cur = l1; tmax = e1; }
-            else {
-                const PlaneCut c1 = leanCut(S, (int)ax1, s1, tmin, e1);
-                if (c1.both) leanPush<RESTART, WIDE>(S, sStack, lStack, c1.lowFirst ? r1 : l1, e1);
-                cur = c1.lowFirst ? l1 : r1; tmax = c1.both ? c1.tp : e1;
-            }
+#if KDPT_LEAN_SKIP_EMPTY == 2
+    for (int trips = 0;; trips++) {
+        if (KDPT_LEAN_TRIP_CAP > 0 && trips == KDPT_LEAN_TRIP_CAP) {       // the round ends without a leaf: idle lanes get their refill
+            S.cur = cur; S.tmin = tmin; S.tmax = tmax;
+            return true;
         }
-        if (((cur >> 27) & 15u) == 15u) {
-            const uint4 nd = KDPT_LDG(T.nodes + (cur & kWideIndexMask));
+        if (WIDE) {
+            if (!(cur & kWideLeaf)) {
+#ifdef KDPT_LEAN_COUNT
+                g_leanSteps++;
+#endif
+                leanWideStep<RESTART>(T, S, sStack, lStack, cur, tmin, tmax);
+                continue;
+            }
+            leanWideLeaf(T, cur, start, count, chunk0);
+        } else {
+            const uint4 nd = leanNode(T, sTop, cur);
+            if ((nd.w & 3u) != kLeafFlag) {
+#ifdef KDPT_LEAN_COUNT
+                g_leanSteps++;
+#endif
+                leanStep<RESTART>(nd, S, sStack, lStack, cur, tmin, tmax);
+                continue;
+            }
             start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
-        } else { start = (int)(cur & kWideIndexMask); count = (int)((cur >> 27) & 15u); }
-    } else {
-        uint4 nd = leanNode(T, sTop, cur);
-        while ((nd.w & 3u) != kLeafFlag) {
-#ifdef KDPT_LEAN_COUNT
-            g_leanSteps++;
-#endif
-            const int a = (int)(nd.w & 3u);
-            const float split = __int_as_float((int)nd.x);
-            const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
-            const bool below = oa < split || (oa == split && da <= 0.0f);
-            const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
-            const float tp = (split - oa) * ia;
-            if (da == 0.0f || tp <= 0.0f || tp >= tmax) cur = nearc;
-            else if (tp <= tmin) cur = farc;
-            else { leanPush<RESTART, WIDE>(S, sStack, lStack, farc, tmax); cur = nearc; tmax = tp; }
-            nd = leanNode(T, sTop, cur);
         }
-        start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
+        if (count > 0) break;
+#ifdef KDPT_LEAN_COUNT
+        g_leanEmpty++;
+#endif
+        S.tmax = tmax;
+        if (!leanPop<RESTART, WIDE>(T, S, H, sStack, lStack)) return false;
+        cur = S.cur; tmin = S.tmin; tmax = S.tmax;
     }
     S.tmax = tmax;
+#else
+    for (;;) {
+        if (WIDE) {
+            while (!(cur & kWideLeaf)) {
 #ifdef KDPT_LEAN_COUNT
-    if (count == 0) g_leanEmpty++;
+                g_leanSteps++;
 #endif
-    if (!KDPT_LEAN_SKIP_EMPTY || count > 0) break;
-    if (!leanPop<RESTART, WIDE>(T, S, H, sStack, lStack)) return false;
-    cur = S.cur; tmin = S.tmin; tmax = S.tmax;
+                leanWideStep<RESTART>(T, S, sStack, lStack, cur, tmin, tmax);
+            }
+            leanWideLeaf(T, cur, start, count, chunk0);
+        } else {
+            uint4 nd = leanNode(T, sTop, cur);
+            while ((nd.w & 3u) != kLeafFlag) {
+#ifdef KDPT_LEAN_COUNT
+                g_leanSteps++;
+#endif
+                leanStep<RESTART>(nd, S, sStack, lStack, cur, tmin, tmax);
+                nd = leanNode(T, sTop, cur);
+            }
+            start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
+        }
+        S.tmax = tmax;
+#ifdef KDPT_LEAN_COUNT
+        if (count == 0) g_leanEmpty++;
+#endif
+        if (!KDPT_LEAN_SKIP_EMPTY || count > 0) break;
+        if (!leanPop<RESTART, WIDE>(T, S, H, sStack, lStack)) return false;
+        cur = S.cur; tmin = S.tmin; tmax = S.tmax;
     }
+#endif
 #ifdef KDPT_LEAN_COUNT
     g_leanRounds++; g_leanTris += count;
 #endif

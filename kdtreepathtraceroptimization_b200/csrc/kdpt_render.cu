@@ -1077,10 +1077,46 @@ static int checkParams(const kdpt_params* p)
     return KDPT_OK;
 }
 
+// KDPT_KDVIZ (pathTraceOneBounceKDbareBoxes, pathtrace.cu:1738-1885): the reference tests the scene's geoms, then every node
+// box with boxIntersectionTestBox — its cube test on matrices made from the box — and gives a box hit the last material. That is
+// the ordinary loop over an extended geom list: the scene's geoms followed by one cube geom per node. Built on first use.
+static int ensureVizScene(kdpt_ctx* ctx)
+{
+    const int numNodes = (int)(ctx->nodeBoxes.size() / 6);
+    const int total = ctx->scene.numGeoms + numNodes;
+    if (ctx->vizCount == total && (ctx->vizGeoms.p || total == 0)) return KDPT_OK;
+    std::vector<kdpt_geom> g((size_t)(total > 0 ? total : 1));
+    std::vector<float> gb(8 * g.size(), 0.f);
+    if (ctx->scene.numGeoms > 0) {
+        KDPT_CUDA(cudaMemcpyAsync(g.data(), ctx->scene.geoms.p, sizeof(kdpt_geom) * (size_t)ctx->scene.numGeoms, cudaMemcpyDeviceToHost, ctx->stream));
+        KDPT_CUDA(cudaMemcpyAsync(gb.data(), ctx->scene.geomBounds.p, sizeof(float) * 8 * (size_t)ctx->scene.numGeoms, cudaMemcpyDeviceToHost, ctx->stream));
+        KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    for (int i = 0; i < numNodes; i++) {
+        kdpt_geom& c = g[(size_t)ctx->scene.numGeoms + i];
+        nodeBoxGeom(&ctx->nodeBoxes[6 * (size_t)i], &ctx->nodeBoxes[6 * (size_t)i + 3], ctx->scene.numMaterials - 1, &c);
+        geomWorldBounds(c.transform, &gb[8 * ((size_t)ctx->scene.numGeoms + i)]);
+    }
+    int rc;
+    if ((rc = ctx->vizGeoms.alloc(sizeof(kdpt_geom) * g.size()))) return rc;
+    if ((rc = ctx->vizBounds.alloc(sizeof(float) * gb.size()))) return rc;
+    KDPT_CUDA(cudaMemcpyAsync(ctx->vizGeoms.p, g.data(), sizeof(kdpt_geom) * g.size(), cudaMemcpyHostToDevice, ctx->stream));
+    KDPT_CUDA(cudaMemcpyAsync(ctx->vizBounds.p, gb.data(), sizeof(float) * gb.size(), cudaMemcpyHostToDevice, ctx->stream));
+    KDPT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->vizCount = total;
+    return KDPT_OK;
+}
+
 static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers& rb, PathSoA P, const Batch& bt, int depth,
                         int stages, kdpt_intersection* dIsects, uint64_t& launches, const GenArgs* gen)
 {
     SceneView S{ctx->scene.geoms.as<kdpt_geom>(), ctx->scene.numGeoms, ctx->scene.geomBounds.as<float4>(), ctx->scene.materials.as<kdpt_material>(), ctx->scene.numMaterials};
+    if (p.mode == KDPT_KDVIZ) {
+        if (ctx->scene.numMaterials < 1) { setError("render: KDPT_KDVIZ needs at least one material (the boxes take the last one)"); return KDPT_ERR_STATE; }
+        int rc = ensureVizScene(ctx);
+        if (rc) return rc;
+        S.geoms = ctx->vizGeoms.as<kdpt_geom>(); S.numGeoms = ctx->vizCount; S.geomBounds = ctx->vizBounds.as<float4>();
+    }
     BounceArgs A; A.iter = bt.iterBase; A.depth = depth; A.stages = stages; A.softness = p.softness; A.enableSss = p.enableSss;
     A.eps = (p.mode == KDPT_FULLSTACK || p.mode == KDPT_REF_T1) ? 0.00001f : 0.0001f;
     int grid = ctx->numSMs * 8;
@@ -1152,6 +1188,12 @@ static int launchBounce(kdpt_ctx* ctx, const kdpt_params& p, const RenderBuffers
     case KDPT_REF_T1: KDPT_LAUNCH_BOUNCE(KDPT_REF_T1); break;
     case KDPT_REF_T2: KDPT_LAUNCH_BOUNCE(KDPT_REF_T2); break;
     case KDPT_BRUTE: KDPT_LAUNCH_BOUNCE(KDPT_BRUTE); break;
+    case KDPT_KDVIZ: {      // no triangles at all: the brute-force instantiation over an empty triangle list
+        Tree none = ctx->tree; none.numNodes = 0; none.numTris = 0; none.numRefNodes = 0;
+        if (gen) bounceKernel<KDPT_BRUTE, true><<<grid, kThreads, 0, s>>>(none, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, *gen);
+        else bounceKernel<KDPT_BRUTE, false><<<grid, kThreads, 0, s>>>(none, S, P, rb.st, A, bt, rb.accum, pc, pa, dIsects, noGen);
+        break;
+    }
     default: KDPT_LAUNCH_BOUNCE(KDPT_BRUTE_BBOX); break;
     }
 #undef KDPT_LAUNCH_BOUNCE

@@ -25,6 +25,7 @@
 
 namespace kdpt {
 void setError(const std::string& msg);
+void nodeBoxGeom(const float* mins, const float* maxs, int materialid, kdpt_geom* out);     // kdpt_internal.h (CUDA-free here)
 // kdpt_build.cu: the same build, level-synchronous on the GPU
 int buildTreeDevice(const float* tri18, const int* mtl, int n, int maxdepth, int device, std::vector<kdpt_node_bare>& nodes,
                     kdpt::BulkVector<kdpt_tri_bare>& tris, kdpt::BulkVector<int>& triSource, float* deviceMs);
@@ -682,6 +683,24 @@ bool attachObj(const std::string& objPath, const std::string& mtlDir, int kdDept
 }
 
 } // namespace
+
+namespace kdpt {
+void nodeBoxGeom(const float* mins, const float* maxs, int materialid, kdpt_geom* g)
+{
+    memset(g, 0, sizeof *g);
+    g->type = 1; g->materialid = materialid;        // CUBE
+    M4 T; memset(&T, 0, sizeof T);
+    for (int a = 0; a < 3; a++) {
+        g->scale[a] = maxs[a] - mins[a];
+        g->translation[a] = (float)((double)(mins[a] + maxs[a]) * 0.5);     // "(mins + maxs) * 0.5" with a double literal
+        T.c[a][a] = g->scale[a]; T.c[3][a] = g->translation[a];
+    }
+    T.c[3][3] = 1.0f;
+    const M4 I = inverse(T), IT = inverseTranspose(T);
+    memcpy(g->transform, T.c, sizeof g->transform); memcpy(g->inverseTransform, I.c, sizeof g->inverseTransform);
+    memcpy(g->invTranspose, IT.c, sizeof g->invTranspose);
+}
+} // namespace kdpt
 
 struct kdpt_host_scene { HostScene s; };
 

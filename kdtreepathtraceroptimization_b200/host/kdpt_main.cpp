@@ -158,6 +158,7 @@ int main(int argc, char** argv)
             if (m == "ref_t2") p.mode = KDPT_REF_T2; else if (m == "ref_t1") p.mode = KDPT_REF_T1;
             else if (m == "shortstack") p.mode = KDPT_SHORTSTACK; else if (m == "fullstack") p.mode = KDPT_FULLSTACK;
             else if (m == "brute") p.mode = KDPT_BRUTE; else if (m == "brute_bbox") p.mode = KDPT_BRUTE_BBOX;
+            else if (m == "kdviz") p.mode = KDPT_KDVIZ;
             else { usage(); return 2; }
         }
         else if (a == "--no-aa") p.antialias = 0;

@@ -49,13 +49,14 @@ void pathtraceFree(Scene*, bool) {}      // pathtrace.cu:274-313; the context li
 
 void pathtrace(uchar4* /*pbo*/, int /*frame*/, int iter, float focalLength, float dofAngle, bool cacherays,
                bool antialias, float softness, bool enableSss, bool testingmode, bool compaction, bool enablekd,
-               bool /*vizkd*/, bool usebbox, bool shortstack) {              // pathtrace.cu:2405-2635
+               bool vizkd, bool usebbox, bool shortstack) {              // pathtrace.cu:2405-2635
     if (!g_ctx) return;                                    // pathtraceInit failed and said so
     kdpt_params p{};
     p.focalLength = focalLength; p.dofAngle = dofAngle; p.softness = softness;
     p.antialias = antialias; p.enableSss = enableSss; p.compaction = compaction; p.testingmode = testingmode;
     p.cacheRays = cacherays;
     p.mode = !enablekd ? (usebbox ? KDPT_BRUTE_BBOX : KDPT_BRUTE)            // key K / key B: pathTraceOneBounce
+           : vizkd ? KDPT_KDVIZ                             // key V: pathTraceOneBounceKDbareBoxes
            : shortstack ? KDPT_REF_T2 : KDPT_REF_T1;       // bit-compatible with traverseKDbare(ShortHybrid);
                                                            // KDPT_SHORTSTACK / KDPT_FULLSTACK give the exact closest hit
     p.sortByMaterial = 1;                                  // the reference sorts in iteration 2 only

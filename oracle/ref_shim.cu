@@ -10,6 +10,7 @@
 //   * the flattened NodeBare[] / TriBare[] arrays  scene.cpp:905-968
 //   * traverseKDbare / traverseKDbareShortHybrid   pathtrace.cu:881-1235
 //   * boxIntersectionTest / sphereIntersectionTest intersections.h:107-203
+//   * boxIntersectionTestBox (the KD-viz mode's node-box test)   intersections.h:51-104
 //   * scatterRay + makeSeededRandomEngine          interactions.h:195-358, pathtrace.cu:62-66
 //   * KDtree(path) -> updateBbox -> split -> writeKDtoFile   KDtree.cpp:37-45,115-135
 //   * pathtraceInit / pathtrace / pathtraceFree on a GPU (only usable on a GPU box)
@@ -156,6 +157,25 @@ int kdref_geom_test(const void* geom_, const float* rays, int n, float* t_out, f
         if (g.type == CUBE) t = boxIntersectionTest(g, r, p, nn, outside);
         else if (g.type == SPHERE) t = sphereIntersectionTest(g, r, p, nn, outside);
         t_out[i] = t;
+        pt_out[3 * i] = p.x; pt_out[3 * i + 1] = p.y; pt_out[3 * i + 2] = p.z;
+        n_out[3 * i] = nn.x; n_out[3 * i + 1] = nn.y; n_out[3 * i + 2] = nn.z;
+        outside_out[i] = outside ? 1 : 0;
+    }
+    return 0;
+}
+
+// boxIntersectionTestBox (what pathTraceOneBounceKDbareBoxes, pathtrace.cu:1738-1885, runs on every node box): box i =
+// mins/maxs[3i..3i+2] against ray i.
+int kdref_box_test_box(const float* mins, const float* maxs, const float* rays, int n, float* t_out, float* pt_out, float* n_out,
+                       unsigned char* outside_out)
+{
+    for (int i = 0; i < n; i++) {
+        Ray r; r.origin = glm::vec3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+        r.direction = glm::vec3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        r.isinside = false; r.sdepth = 0.f;
+        float mn[3] = {mins[3 * i], mins[3 * i + 1], mins[3 * i + 2]}, mx[3] = {maxs[3 * i], maxs[3 * i + 1], maxs[3 * i + 2]};
+        glm::vec3 p(0.f), nn(0.f); bool outside = true;
+        t_out[i] = boxIntersectionTestBox(mn, mx, r, p, nn, outside);
         pt_out[3 * i] = p.x; pt_out[3 * i + 1] = p.y; pt_out[3 * i + 2] = p.z;
         n_out[3 * i] = nn.x; n_out[3 * i + 1] = nn.y; n_out[3 * i + 2] = nn.z;
         outside_out[i] = outside ? 1 : 0;

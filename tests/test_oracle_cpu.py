@@ -165,6 +165,25 @@ def test_analytic_geoms_match_reference(oracle, golden):
     assert nhit > 40
 
 
+def test_kdviz_node_box_test_matches_reference(oracle):
+    """boxIntersectionTestBox (intersections.h:51-104), what the KD-viz mode runs on every node box: the oracle's cube geom of a
+    box (glm::inverse restated) through its cube test equals the reference function's outputs bit for bit
+    (tests/golden/kdviz_boxes.npz, made by make_golden_kdviz.py from the unmodified reference)"""
+    g = np.load(os.path.join(GOLDEN, "kdviz_boxes.npz"))
+    oracle.lib.ko_box_test_box.restype = ctypes.c_float
+    nhit = 0
+    for i in range(len(g['rays'])):
+        pt = np.zeros(3, 'f4'); nr = np.zeros(3, 'f4'); outside = ctypes.c_int(1)
+        t = oracle.lib.ko_box_test_box(P(g['mins'][i].copy()), P(g['maxs'][i].copy()), P(g['rays'][i, :3].copy()), P(g['rays'][i, 3:].copy()),
+                                       P(pt), P(nr), ctypes.byref(outside))
+        assert bits(np.float32(t)) == bits(g['t'][i]) or (np.isnan(t) and np.isnan(g['t'][i])), i
+        if t > 0:
+            nhit += 1
+            assert (bits(pt) == bits(g['point'][i])).all() and (bits(nr) == bits(g['normal'][i])).all(), i
+            assert outside.value == g['outside'][i]
+    assert nhit > 2500
+
+
 def test_scatter_matches_reference(oracle, golden):
     """scatterRay (interactions.h:195-358) on every scene material + synthetic mirror / glass / SSS materials, with and
     without softness; same glibc on both sides, so bit-for-bit"""
