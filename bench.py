@@ -566,7 +566,7 @@ def main():
     out = None
     check = {"ok": None}
     if rank == 0:
-        # ---- roofline of the dominant kernel (bounceKernel): live CUDA-event durations via TESTINGMODE ----
+        # ---- roofline of the dominant kernels (the bounce: front + lean traversal + finish): live CUDA-event durations via TESTINGMODE ----
         roof = None; cpu = None; extras = {}
         ab = {}
         try:
@@ -578,7 +578,9 @@ def main():
             launch_ms = st["intersect_ms"] / nb
             bytes_per_launch = ab["bytes_per_ray_bounce"] * st["ray_bounces"] / nb
             ws = ctx.tree_info()["device_bytes"] + 2 * 56 * npix * min(S, 64)
-            roof = roofline_object(args.workload, "bounceKernel<%s>" % mode_name, bytes_per_launch, launch_ms, ws,
+            kname = ("frontKernel + traceQueueKernel<%s> + finishQueueKernel (one bounce, wavefront form)" if ctx.refined_info()["num_nodes"] > 0 and mode_name in ("fullstack", "shortstack")
+                     else "bounceKernel<%s>") % mode_name
+            roof = roofline_object(args.workload, kname, bytes_per_launch, launch_ms, ws,
                                    {"kernel_share_of_step": st["intersect_ms"] / st["total_ms"],
                                     "algorithmic_bytes_per_ray_bounce": ab["bytes_per_ray_bounce"],
                                     "per_ray_bounce": {k: ab.get(k) for k in ("V", "B", "T", "H", "traversal_bytes", "path_bytes")},

@@ -196,9 +196,9 @@ typedef struct {
                                    tested warp-cooperatively through chunk boxes); > 0: leaf size at which splitting stops */
     float refineTraversalCost;  /* <= 0: default (2.0); cost of one node step relative to one triangle test in the builder's
                                    surface-area heuristic */
-    int nodeForm;               /* how the exact modes' tree is laid out for their kernel. 0: default; 1: one 16-byte record per
-                                   node; 2: two levels per 32-byte record, small leaves named inline by their parents (half the
-                                   dependent loads of a descent) */
+    int nodeForm;               /* how the exact modes' tree is laid out for their kernel. 1: one 16-byte record per node; 2: two
+                                   levels per 32-byte record, small leaves named inline by their parents (half the dependent
+                                   loads of a descent; faster once the tree exceeds the L2, slower below); 0: chosen by size */
     int reserved[5];
 } kdpt_build_opts;
 int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts* opts, kdpt_ctx** out);
@@ -211,6 +211,11 @@ int kdpt_tree_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* ma
 
 /* the tree the exact modes walk (== kdpt_tree_info's numbers when refinement is off) */
 int kdpt_refined_info(const kdpt_ctx* ctx, int* numNodes, int* numLeafTris, int* maxDepth, int* maxLeaf);
+
+/* KDPT_KDVIZ draws node i as this geom: the cube boxIntersectionTestBox (src/intersections.h:51-66) makes of nodes[i].mins /
+ * .maxs — scale = extent, translation = centre, transform / inverse as glm builds them — with the given material. Host-only
+ * helper (no GPU needed): a caller that wants the boxes of some levels only can append such geoms to its own scene. */
+int kdpt_node_box_geom(const float mins[3], const float maxs[3], int materialid, kdpt_geom* out);
 
 /* n rays in, n hits out, HOST buffers (H2D + kernel + D2H). t_min_in may be NULL (FLT_MAX). */
 int kdpt_trace(kdpt_ctx* ctx, const kdpt_ray* rays, const float* t_min_in, int n, kdpt_hit* hits, int mode);

@@ -103,6 +103,7 @@ def load_library() -> ctypes.CDLL:
     lib.kdpt_create_opts.argtypes = [ctypes.POINTER(_CScene), ci, ctypes.POINTER(CBuildOpts), ctypes.POINTER(vp)]
     lib.kdpt_refined_info.argtypes = [vp] + [ctypes.POINTER(ci)] * 4
     lib.kdpt_destroy.argtypes = [vp]
+    lib.kdpt_node_box_geom.argtypes = [vp, vp, ci, vp]
     lib.kdpt_tree_info.argtypes = [vp] + [ctypes.POINTER(ci)] * 4 + [ctypes.POINTER(ctypes.c_uint64)]
     lib.kdpt_trace.argtypes = [vp, vp, vp, ci, vp, ci]
     lib.kdpt_trace_device.argtypes = [vp, vp, vp, ci, vp, ci, vp]
@@ -144,6 +145,16 @@ def load_library() -> ctypes.CDLL:
 def _check(rc: int, what: str):
     if rc != 0:
         raise KdptError(f"{what} failed ({rc}): {load_library().kdpt_last_error().decode(errors='replace')}")
+
+
+def node_box_geoms(nodes: np.ndarray, materialid: int) -> np.ndarray:
+    """kdpt_node_box_geom for every node: the cube geoms KDPT_KDVIZ draws (host-only helper)"""
+    lib = load_library()
+    out = np.zeros(len(nodes), GEOM)
+    for i in range(len(nodes)):
+        mn = np.ascontiguousarray(nodes['mins'][i], 'f4'); mx = np.ascontiguousarray(nodes['maxs'][i], 'f4')
+        _check(lib.kdpt_node_box_geom(mn.ctypes.data, mx.ctypes.data, int(materialid), out[i:i + 1].ctypes.data), "kdpt_node_box_geom")
+    return out
 
 
 @dataclass

@@ -68,6 +68,28 @@ static int upload(DeviceBuffer& buf, const V& v, const T** devPtr, cudaStream_t 
 
 } // namespace kdpt
 
+namespace kdpt {
+void geomWorldBounds(const float* m, float* lohi8)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+    for (int c = 0; c < 8; c++) {
+        double x = (c & 1) ? 0.5 : -0.5, y = (c & 2) ? 0.5 : -0.5, z = (c & 4) ? 0.5 : -0.5;
+        for (int a = 0; a < 3; a++) {
+            double v = (double)m[a] * x + (double)m[4 + a] * y + (double)m[8 + a] * z + (double)m[12 + a];
+            if (!(v == v) || !(fabs(v) < 1e30)) bad = true;
+            lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a];
+        }
+    }
+    for (int a = 0; a < 3; a++) {
+        double pad = 2e-3 + 1e-4 * (hi[a] - lo[a]) + 1e-5 * (fabs(lo[a]) > fabs(hi[a]) ? fabs(lo[a]) : fabs(hi[a]));
+        lohi8[a] = bad ? -INFINITY : (float)(lo[a] - pad);         // degenerate transform: never cull
+        lohi8[4 + a] = bad ? INFINITY : (float)(hi[a] + pad);
+    }
+    lohi8[3] = lohi8[7] = 0.f;
+}
+} // namespace kdpt
+
 using namespace kdpt;
 
 extern "C" {
@@ -124,27 +146,6 @@ int kdpt_destroy(kdpt_ctx* ctx)
     return KDPT_OK;
 }
 
-namespace kdpt {
-void geomWorldBounds(const float* m, float* lohi8)
-{
-    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    bool bad = false;
-    for (int c = 0; c < 8; c++) {
-        double x = (c & 1) ? 0.5 : -0.5, y = (c & 2) ? 0.5 : -0.5, z = (c & 4) ? 0.5 : -0.5;
-        for (int a = 0; a < 3; a++) {
-            double v = (double)m[a] * x + (double)m[4 + a] * y + (double)m[8 + a] * z + (double)m[12 + a];
-            if (!(v == v) || !(fabs(v) < 1e30)) bad = true;
-            lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a];
-        }
-    }
-    for (int a = 0; a < 3; a++) {
-        double pad = 2e-3 + 1e-4 * (hi[a] - lo[a]) + 1e-5 * (fabs(lo[a]) > fabs(hi[a]) ? fabs(lo[a]) : fabs(hi[a]));
-        lohi8[a] = bad ? -INFINITY : (float)(lo[a] - pad);         // degenerate transform: never cull
-        lohi8[4 + a] = bad ? INFINITY : (float)(hi[a] + pad);
-    }
-    lohi8[3] = lohi8[7] = 0.f;
-}
-} // namespace kdpt
 
 int kdpt_create(const kdpt_scene* scene, int device, kdpt_ctx** out) { return kdpt_create_opts(scene, device, nullptr, out); }
 
@@ -281,6 +282,13 @@ int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts*
     flat.entryOf.clear(); flat.entryOf.shrink_to_fit();
     ctx->info = flat;
     *out = ctx;
+    return KDPT_OK;
+}
+
+int kdpt_node_box_geom(const float mins[3], const float maxs[3], int materialid, kdpt_geom* out)
+{
+    if (!mins || !maxs || !out) { setError("kdpt_node_box_geom: null argument"); return KDPT_ERR_ARG; }
+    nodeBoxGeom(mins, maxs, materialid, out);
     return KDPT_OK;
 }
 

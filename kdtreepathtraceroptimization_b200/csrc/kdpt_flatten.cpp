@@ -566,7 +566,7 @@ bool flatten(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tri
         fillHot(xorder, tris, canon, nthreads, out.xtriA, out.xtriB, out.xtriC);
         out.entryOf.resize(numTris);
         parallelFor(numTris, nthreads, [&](int lo, int hi) { for (int i = lo; i < hi; i++) out.entryOf[order[i]] = i; });
-        if (opts.wideNodes) buildWide(out);
+        if (opts.wideNodes > 0 || (opts.wideNodes < 0 && out.bytes() >= kWideMinBytes)) buildWide(out);
         if (opts.topLevels > 0) {
             // breadth-first copy of the first topLevels levels (at most 2^levels - 1 nodes)
             const int levels = opts.topLevels > 11 ? 11 : opts.topLevels;

@@ -48,10 +48,13 @@ struct FlatTree {
     uint64_t bytes() const;
 };
 
+constexpr uint64_t kWideMinBytes = 100ull << 20;     // two-level records pay once the tree exceeds the L2 (kdpt_lean.cuh)
+
 struct FlattenOpts {
     int refineLeafMax = 8;      // leaves with more triangles than this are split further for the exact modes; 0 = off
     float traversalCost = 2.0f; // SAH: cost of one node step relative to one triangle test
-    int wideNodes = 0;          // also emit the refined tree as two-level records with the small leaves named inline by their parents
+    int wideNodes = -1;         // also emit the refined tree as two-level records with the small leaves named inline by their parents
+                                // (what the exact modes' kernel then walks): 1 yes, 0 no, -1 when the device arrays reach kWideMinBytes
     int topLevels = 0;          // levels of the refined tree copied breadth-first for shared-memory staging (0 = none, <= 11)
     FlattenOpts();              // defaults, overridable in development by KDPT_REFINE_LEAF / KDPT_REFINE_CT
 };

@@ -28,12 +28,6 @@ namespace kdpt {
 #define KDPT_LEAN_REFILL_MIN 8      // idle lanes needed before the warp fetches new rays (while rays are left): the fetch
                                     // code runs with only the idle lanes active (1 / 4 / 8: 1623 / 1695 / 1722 Mrays/s on dragon1m)
 #endif
-#ifndef KDPT_LEAN_SKIP_EMPTY
-#define KDPT_LEAN_SKIP_EMPTY 0      // what a lane does at an empty leaf: 0 end the round, 1 / 2 pop inside the descent (see leanRoundLeaf)
-#endif
-#ifndef KDPT_LEAN_TRIP_CAP
-#define KDPT_LEAN_TRIP_CAP 0        // KDPT_LEAN_SKIP_EMPTY == 2: a round also ends after this many loop trips without a leaf (0: no cap)
-#endif
 constexpr int kLeanThreads = KDPT_LEAN_THREADS;
 constexpr int kLeanSmemStack = KDPT_LEAN_SMEM_STACK;
 constexpr int kLeanRing = 8;        // RESTART: entries in the ring
@@ -49,8 +43,11 @@ constexpr int kLeanRing = 8;        // RESTART: entries in the ring
 // where a child axis of 3 means "this child is a leaf" and its first slot names it. A reference is either a record index or
 //   kWideLeaf | count << 27 | first entry    (count <= 14: the leaf's range inline — no record to fetch, an empty leaf costs nothing)
 //   kWideLeaf | 15 << 27 | xnodes index      (chunked or bigger leaves: their 16-byte leaf record)
-// One fetch decides two levels, so a descent is half as many dependent loads; the far subtrees of both levels are cut by
-// their planes at once and go to the stack as up to three (reference, exit distance) entries, farthest first.
+// One fetch decides two levels, so a descent is half as many dependent loads (dragon_5: 29 -> 12 per ray, leaf records included);
+// the far subtrees of both levels are cut by their planes at once and go to the stack as up to three (reference, exit
+// distance) entries, farthest first. Measured (profiles/r2_call20_empty_leaf_policies.txt): +6-10 % on the 10 M soup, +2 % on
+// the 1 M soup, +-1 % on the 1.6 M dragon, -2 to -5 % on trees that live in L1/L2 (dragon_5, bunny) where the extra plane
+// arithmetic costs more than the saved loads — so kdpt_create picks this form only for trees beyond the L2 (kWideMinBytes).
 constexpr unsigned kWideLeaf = 0x80000000u;
 constexpr unsigned kWideIndexMask = (1u << 27) - 1u;
 constexpr int kWideStack = 48;      // 3 entries per record level, at most 16 record levels (buildWide refuses deeper trees)
@@ -317,10 +314,12 @@ KDPT_HD void leanStep(const uint4 nd, LeanState& S, uint2* sStack, uint2* lStack
 // experiment"): the lanes that walk on before their tests are done prune with a stale best hit; and the same dealing
 // without speculation (commit "dealt leaf tests experiment") costs in scans and shared-memory traffic what it returns.
 //
-// KDPT_LEAN_SKIP_EMPTY: what a lane does at an EMPTY leaf (the surface-area heuristic cuts empty space off: two leaves of
-// three a ray enters on dragon_5 are empty). 0: the round ends there like at any leaf. 1: it pops and descends again before
-// the warp moves on to the triangles (descent loop nested in a pop loop). 2: the same in ONE loop whose trips are either a
-// node step or a pop, so that a lane never waits for the other lanes' descents before it pops.
+// Empty leaves (the surface-area heuristic cuts empty space off: two leaves of three a ray enters on dragon_5 are empty) end a
+// lane's round like any other leaf. Popping them inside the descent — nested in a pop loop, or as ONE loop whose trips are a
+// node step or a pop, with or without a cap on the trips — cuts the rounds per ray from 5.8 to 1.9 and was measured 8-20 %
+// SLOWER on every workload (profiles/r2_call19_*.txt, r2_call20_*.txt; code: commit "empty-leaf policies of the lean loop"):
+// the rounds get as long as the longest chain of descents among the lanes, finished lanes wait that much longer for their
+// refill, and the pop code joins the divergent part of the loop.
 template <bool RESTART, bool WIDE = false>
 KDPT_HD bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, float eps, uint2* sStack, uint2* lStack,
                            const uint4* sTop)
@@ -328,73 +327,28 @@ KDPT_HD bool leanRoundLeaf(const Tree& T, bool alive, LeanState& S, Hit& H, floa
     if (!alive) return false;
     unsigned cur = S.cur; float tmin = S.tmin, tmax = S.tmax;
     int start, count; unsigned chunk0 = kNoChunks;
-#if KDPT_LEAN_SKIP_EMPTY == 2
-    for (int trips = 0;; trips++) {
-        if (KDPT_LEAN_TRIP_CAP > 0 && trips == KDPT_LEAN_TRIP_CAP) {       // the round ends without a leaf: idle lanes get their refill
-            S.cur = cur; S.tmin = tmin; S.tmax = tmax;
-            return true;
+    if (WIDE) {
+        while (!(cur & kWideLeaf)) {
+#ifdef KDPT_LEAN_COUNT
+            g_leanSteps++;
+#endif
+            leanWideStep<RESTART>(T, S, sStack, lStack, cur, tmin, tmax);
         }
-        if (WIDE) {
-            if (!(cur & kWideLeaf)) {
+        leanWideLeaf(T, cur, start, count, chunk0);
+    } else {
+        uint4 nd = leanNode(T, sTop, cur);
+        while ((nd.w & 3u) != kLeafFlag) {
 #ifdef KDPT_LEAN_COUNT
-                g_leanSteps++;
+            g_leanSteps++;
 #endif
-                leanWideStep<RESTART>(T, S, sStack, lStack, cur, tmin, tmax);
-                continue;
-            }
-            leanWideLeaf(T, cur, start, count, chunk0);
-        } else {
-            const uint4 nd = leanNode(T, sTop, cur);
-            if ((nd.w & 3u) != kLeafFlag) {
-#ifdef KDPT_LEAN_COUNT
-                g_leanSteps++;
-#endif
-                leanStep<RESTART>(nd, S, sStack, lStack, cur, tmin, tmax);
-                continue;
-            }
-            start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
+            leanStep<RESTART>(nd, S, sStack, lStack, cur, tmin, tmax);
+            nd = leanNode(T, sTop, cur);
         }
-        if (count > 0) break;
-#ifdef KDPT_LEAN_COUNT
-        g_leanEmpty++;
-#endif
-        S.tmax = tmax;
-        if (!leanPop<RESTART, WIDE>(T, S, H, sStack, lStack)) return false;
-        cur = S.cur; tmin = S.tmin; tmax = S.tmax;
+        start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
     }
     S.tmax = tmax;
-#else
-    for (;;) {
-        if (WIDE) {
-            while (!(cur & kWideLeaf)) {
 #ifdef KDPT_LEAN_COUNT
-                g_leanSteps++;
-#endif
-                leanWideStep<RESTART>(T, S, sStack, lStack, cur, tmin, tmax);
-            }
-            leanWideLeaf(T, cur, start, count, chunk0);
-        } else {
-            uint4 nd = leanNode(T, sTop, cur);
-            while ((nd.w & 3u) != kLeafFlag) {
-#ifdef KDPT_LEAN_COUNT
-                g_leanSteps++;
-#endif
-                leanStep<RESTART>(nd, S, sStack, lStack, cur, tmin, tmax);
-                nd = leanNode(T, sTop, cur);
-            }
-            start = (int)nd.x; count = (int)nd.y; chunk0 = nd.z;
-        }
-        S.tmax = tmax;
-#ifdef KDPT_LEAN_COUNT
-        if (count == 0) g_leanEmpty++;
-#endif
-        if (!KDPT_LEAN_SKIP_EMPTY || count > 0) break;
-        if (!leanPop<RESTART, WIDE>(T, S, H, sStack, lStack)) return false;
-        cur = S.cur; tmin = S.tmin; tmax = S.tmax;
-    }
-#endif
-#ifdef KDPT_LEAN_COUNT
-    g_leanRounds++; g_leanTris += count;
+    g_leanRounds++; g_leanTris += count; if (count == 0) g_leanEmpty++;
 #endif
     if (count > 0) {
         if (chunk0 == kNoChunks) {

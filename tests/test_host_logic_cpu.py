@@ -152,6 +152,19 @@ def test_flatten_rejects_malformed_trees(hostsim, golden_all):
     assert run(bad, g['tris']) == -1
 
 
+def test_kdviz_node_geoms_equal_the_oracles(oracle, golden_all):
+    """kdpt_node_box_geom (what KDPT_KDVIZ draws for a node) builds the matrices of boxIntersectionTestBox exactly like the
+    oracle, whose cube test on them is pinned to the reference's outputs (test_kdviz_node_box_test_matches_reference): transform
+    and inverse byte for byte on every node of every fixture tree. Host-only, no GPU."""
+    for name, g in golden_all.items():
+        nodes = np.ascontiguousarray(g['nodes'])
+        mine = kdpt.node_box_geoms(nodes, 5)
+        ref = np.zeros(len(nodes), kdpt.GEOM)
+        oracle.lib.ko_kdviz_geoms(P(nodes), len(nodes), 6, P(ref))
+        for k in ('type', 'materialid', 'transform', 'inverseTransform', 'translation', 'scale'):
+            assert mine[k].tobytes() == ref[k].tobytes(), (name, k)
+
+
 def test_c_abi_exports_every_declared_symbol():
     """libkdpt.so loads on a machine without a GPU and exports what include/kdpt.h declares; compute calls fail
     loudly (no CPU fallback)."""

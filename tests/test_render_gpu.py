@@ -403,3 +403,35 @@ def test_ray_cache_and_brute_force_modes(oracle):
     assert (np.abs(cached - o).max(2) < 1e-3).mean() > 0.995
     assert imgs[kdpt.BRUTE].tobytes() == imgs[kdpt.SHORTSTACK].tobytes()
     assert imgs[kdpt.BRUTE_BBOX].tobytes() == imgs[kdpt.SHORTSTACK].tobytes()
+
+
+def test_kdviz_mode(oracle):
+    """KDPT_KDVIZ (VIZKD, pathTraceOneBounceKDbareBoxes pathtrace.cu:1738-1885): the scene's geoms, then every node box as a cube of
+    the last material, no triangles. (a) The mode equals, bit for bit, an ordinary render of the scene rewritten that way by
+    hand — geoms + kdpt_node_box_geom cubes, no tree; (b) that render equals the oracle's of the same rewritten scene (node
+    cubes from the oracle's own ko_kdviz_geoms, whose test is pinned to the reference's boxIntersectionTestBox outputs) within
+    the render loop's libm tolerance."""
+    import dataclasses
+    for name, res, iters in (("cornell8_stanford_bunny.npz", 96, 3), ("cornell_dragon_5.npz", 48, 2)):
+        sc = _scene(name, res, res)
+        p = kdpt.default_params(mode=kdpt.KDVIZ)
+        with kdpt.Context(sc) as ctx:
+            ctx.clear_image(); st = ctx.render(1, iters, 1, p); viz = ctx.image()
+            ctx.clear_image(); ctx.render(1, iters, 1, kdpt.default_params(mode=kdpt.REF_T2)); plain = ctx.image()
+            with pytest.raises(kdpt.KdptError):
+                ctx.trace(np.zeros((4, 6), 'f4'), None, kdpt.KDVIZ)        # a render-loop mode only
+        assert not np.array_equal(viz, plain)
+        cubes = kdpt.node_box_geoms(sc.nodes, len(sc.materials) - 1)
+        by_hand = dataclasses.replace(sc, nodes=np.zeros(0, kdpt.NODE), tris=np.zeros(0, kdpt.TRI), geoms=np.concatenate([sc.geoms, cubes]))
+        q = kdpt.default_params(mode=kdpt.REF_T2)
+        with kdpt.Context(by_hand) as ctx:
+            ctx.clear_image(); st2 = ctx.render(1, iters, 1, q); hand = ctx.image()
+        assert viz.tobytes() == hand.tobytes() and int(st['ray_bounces']) == int(st2['ray_bounces'])
+        ocubes = np.zeros(len(sc.nodes), kdpt.GEOM)
+        oracle.lib.ko_kdviz_geoms(P(sc.nodes), len(sc.nodes), len(sc.materials), P(ocubes))
+        osc = dataclasses.replace(by_hand, geoms=np.concatenate([sc.geoms, ocubes]))
+        o, total = _oracle_render(oracle, osc, q, list(range(1, iters + 1)))
+        assert abs(int(st['ray_bounces']) - int(total)) <= max(2, int(2e-3 * total)), (st['ray_bounces'], total)
+        rmse = float(np.sqrt(np.mean((viz.astype('f8') - o) ** 2)))
+        assert rmse < 0.02 * max(float(o.mean()), 1e-3), rmse
+        assert (np.abs(viz - o).max(2) < 1e-3).mean() > 0.99
