@@ -12,6 +12,12 @@
  * the calling thread's last failure. Nothing here ever calls exit() (the reference's checkCUDAError does,
  * pathtrace.cu:38-60). There is no CPU fallback: without a usable CUDA device every entry point fails with
  * KDPT_ERR_CUDA.
+ *
+ * Process-wide effects a host that drives several GPUs from one thread should know: every call that takes a context makes
+ * that context's device the calling thread's current device (cudaSetDevice) and leaves it so — restoring a "previous" device
+ * would create a primary context on device 0 in every process that never chose one; device memory comes from the device's
+ * default stream-ordered pool, whose release threshold the library lifts (freed blocks stay cached for the next
+ * pathtraceInit; cudaMemPoolTrimTo on that pool gives them back).
  */
 #ifndef KDPT_H
 #define KDPT_H
@@ -198,7 +204,8 @@ typedef struct {
                                    surface-area heuristic */
     int nodeForm;               /* how the exact modes' tree is laid out for their kernel. 1: one 16-byte record per node; 2: two
                                    levels per 32-byte record, small leaves named inline by their parents (half the dependent
-                                   loads of a descent; faster once the tree exceeds the L2, slower below); 0: chosen by size */
+                                   loads of a descent; faster once the tree is several times the L2, slower below); 0: chosen by size
+                                   (two-level from 1 GB of device arrays on) */
     int reserved[5];
 } kdpt_build_opts;
 int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts* opts, kdpt_ctx** out);
