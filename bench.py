@@ -373,7 +373,9 @@ def run_trace_workload(args):
                    "sample": "the first %d of the same rays through the reference's traverseKDbare semantics (oracle restatement, "
                              "the reference's own function overflows nodeIDs[4000] on this tree), %.1f s" % (kcpu, dt1)}
         ws = ctx.tree_info()["device_bytes"]
-        roof = roofline_object(args.workload, "traceKernel<%s>" % (args.mode or "fullstack"), ab["bytes_per_ray_bounce"] * nrays, ms / K, ws,
+        tmode = args.mode or "fullstack"
+        kname = ("traceLeanKernel<%s>" if tmode in ("fullstack", "shortstack") and ctx.refined_info()["num_nodes"] > 0 else "traceKernel<%s>") % tmode
+        roof = roofline_object(args.workload, kname, ab["bytes_per_ray_bounce"] * nrays, ms / K, ws,
                                {"algorithmic_bytes_per_ray": ab["bytes_per_ray_bounce"], "per_ray": {k: ab.get(k) for k in ("V", "B", "T", "H")},
                                 "unculled_reference_tree_bytes_per_ray": ab.get("unculled", {}).get("bytes_per_ray_bounce")}, units_per_launch=nrays)
         line = {"metric": "Mrays/s (traverse+intersect)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
