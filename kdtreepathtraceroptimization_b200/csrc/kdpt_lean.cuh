@@ -13,6 +13,9 @@
 // kLeanSmemStack entries per lane live in shared memory ([depth][thread]: conflict-free whatever the depths), deeper
 // ones in local memory. RESTART (the short-stack mode): shared-memory ring only; a push onto a full ring drops the
 // OLDEST (farthest) entry, and a ray that runs out of entries after a drop restarts at the root from where it is.
+//
+// Like kdpt_core.cuh this header also compiles with g++ (KDPT_HD): tests/hostsim runs leanBegin / leanRound ray by ray on the
+// CPU against the brute-force oracle, for both node forms and both stack forms.
 #pragma once
 #include "kdpt_core.cuh"
 

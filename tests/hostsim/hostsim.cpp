@@ -99,6 +99,53 @@ extern "C" int hostsim_refined_info(const kdpt_node_bare* nodes, int numNodes, c
     return 0;
 }
 
+// the two-level records against the 16-byte nodes they were made from: the same tree — planes, axes, leaves (inline range or record
+// index) — reached through the records; returns the number of leaves reached, or -(1 + the first node that differs)
+static long wideCheck(const FlatTree& F, uint32_t ref, uint32_t id)
+{
+    const HostNode& n = F.xnodes[id];
+    if (ref & kWideLeaf) {
+        if ((n.w & 3u) != 3u) return -(long)(1 + id);
+        const unsigned cnt = (ref >> 27) & 15u, idx = ref & kWideIndexMask;
+        if (cnt == 15u) return idx == id ? 1 : -(long)(1 + id);
+        if (n.z != kNoChunks || n.y != cnt || (cnt && n.x != idx)) return -(long)(1 + id);
+        return 1;
+    }
+    if ((n.w & 3u) == 3u || 2 * (size_t)ref + 1 >= F.xwide.size()) return -(long)(1 + id);
+    const HostNode &A = F.xwide[2 * (size_t)ref], &B = F.xwide[2 * (size_t)ref + 1];
+    if (A.x != n.x || (A.w & 3u) != (n.w & 3u)) return -(long)(1 + id);
+    long leaves = 0;
+    const uint32_t kid[2] = {n.z, n.y}, slot[2][2] = {{B.x, B.y}, {B.z, B.w}}, split[2] = {A.y, A.z};
+    for (int k = 0; k < 2; k++) {
+        const HostNode& c = F.xnodes[kid[k]];
+        const unsigned ax = (A.w >> (2 + 2 * k)) & 3u;
+        if (ax != (c.w & 3u)) return -(long)(1 + kid[k]);
+        long r;
+        if (ax == 3u) r = wideCheck(F, slot[k][0], kid[k]);
+        else {
+            if (split[k] != c.x) return -(long)(1 + kid[k]);
+            r = wideCheck(F, slot[k][0], c.z);
+            if (r < 0) return r;
+            leaves += r;
+            r = wideCheck(F, slot[k][1], c.y);
+        }
+        if (r < 0) return r;
+        leaves += r;
+    }
+    return leaves;
+}
+extern "C" long hostsim_wide_check(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, int leafMax, long long* info)
+{
+    FlatTree F; std::string err;
+    FlattenOpts fo; fo.wideNodes = 1; if (leafMax >= 0) fo.refineLeafMax = leafMax;
+    if (!flatten(nodes, numNodes, tris, numTris, F, err, fo)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+    if (F.xwide.empty()) return -2;
+    long leavesInNodes = 0;
+    for (const HostNode& h : F.xnodes) if ((h.w & 3u) == 3u) leavesInNodes++;
+    if (info) { info[0] = (long long)F.xnodes.size(); info[1] = (long long)F.xwide.size() / 2; info[2] = leavesInNodes; }
+    return wideCheck(F, F.xwideRoot, 0);
+}
+
 // canonical index of every TriBare entry as the product's flatten computes it (what kdpt_hit.tri reports)
 extern "C" int hostsim_canonical(const kdpt_node_bare* nodes, int numNodes, const kdpt_tri_bare* tris, int numTris, int* canonOut)
 {

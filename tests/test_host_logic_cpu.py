@@ -92,6 +92,52 @@ def test_refined_tree_shape(hostsim, golden_all):
         assert entries <= 8 * len(g['tris'])
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_lean_loop_on_random_soups(hostsim, oracle, seed):
+    """clustered random triangles with exact duplicates, zero-area and axis-aligned ones (deep refinement, empty cells, leaves the
+    refinement cannot split): the lean loop in all four forms and the packet form vs brute force, rays from inside and outside"""
+    rng = np.random.default_rng(seed)
+    n = 2500
+    centres = rng.uniform(-1, 1, (12, 3))
+    c = centres[rng.integers(0, 12, n)] + rng.normal(scale=0.08, size=(n, 3))
+    e1 = rng.normal(scale=0.03, size=(n, 3)); e2 = rng.normal(scale=0.03, size=(n, 3))
+    e2[:40] = e1[:40] * 2                                   # zero area
+    e1[40:80, 2] = 0; e2[40:80, 2] = 0                      # axis-aligned (flat boxes before padding)
+    v = np.concatenate([c, c + e1, c + e2], 1).astype('f4')
+    v[100:160] = v[200:260]                                 # exact duplicates (canonical index = the smaller one)
+    v[300:500] = v[300]                                     # 200 copies of one triangle: a leaf no plane can split
+    nr = rng.normal(size=(n, 9)).astype('f4')
+    nr[100:160] = nr[200:260]; nr[300:500] = nr[300]
+    nodes, tris, _ = oracle.build_tree(np.concatenate([v, nr], 1), None, 13)
+    m = 3000
+    d = rng.normal(size=(m, 3))
+    o = np.where(rng.random((m, 1)) < 0.5, rng.uniform(-1.2, 1.2, (m, 3)), 3 * d / np.linalg.norm(d, axis=1, keepdims=True))
+    tgt = centres[rng.integers(0, 12, m)] + rng.normal(scale=0.1, size=(m, 3))
+    d = np.where(rng.random((m, 1)) < 0.7, tgt - o, d)
+    rays = np.concatenate([o, d], 1).astype('f4')
+    g = dict(nodes=nodes, tris=tris, rays=rays)
+    ref = {om: oracle.trace(om, nodes, tris, rays, None, 1) for om in (KO_BRUTE_T1, KO_BRUTE_T2)}
+    assert (ref[KO_BRUTE_T1]['hit'] > 0).sum() > 300
+    for mode, om in ((kdpt.FULLSTACK, KO_BRUTE_T1), (kdpt.SHORTSTACK, KO_BRUTE_T2), (LEAN_FULL, KO_BRUTE_T1), (LEAN_RESTART, KO_BRUTE_T2),
+                     (LEAN_WIDE_FULL, KO_BRUTE_T1), (LEAN_WIDE_RESTART, KO_BRUTE_T2)):
+        for refine in (-1, 2):
+            k, _, _ = _sim(hostsim, g, mode, nmat=1, refine=refine)
+            assert_hits_equal(k, ref[om], tris, f"seed {seed} mode {mode} refine {refine}")
+
+
+def test_two_level_records_encode_the_same_tree(hostsim, golden_all):
+    """kdpt_flatten.cpp:buildWide against the 16-byte nodes it was made from: walking the records reaches every leaf of the refined
+    tree exactly once, with the same planes and axes on the way and the same leaf ranges (inline or by record index)"""
+    hostsim.hostsim_wide_check.restype = ctypes.c_long
+    for name, g in golden_all.items():
+        for leaf in (-1, 1, 16):
+            info = np.zeros(3, 'i8')
+            got = hostsim.hostsim_wide_check(P(g['nodes']), len(g['nodes']), P(g['tris']), len(g['tris']), leaf, P(info))
+            nodes, records, leaves = (int(x) for x in info)
+            assert got == leaves > 0, (name, leaf, got, leaves)
+            assert records <= (nodes - leaves + 1) // 2 + 1 + leaves // 2, (name, nodes, records)     # about one record per two interior nodes
+
+
 def test_degenerate_rays(hostsim, oracle, golden_all):
     g = golden_all["cornell8_stanford_bunny.npz"]
     lo, hi = g['nodes']['mins'][0], g['nodes']['maxs'][0]
