@@ -109,6 +109,23 @@ KDPT_HD unsigned rayBinKey(const Tree& T, V3 o, V3 d)
     return node * 8u + ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
 }
 
+// component k of a vector for the descent: two selects. Written as PTX because the compiler turns comp()'s nested conditional for
+// the three vectors of a plane test into a branch on the axis — three-way divergence in the middle of every node step.
+KDPT_HD float compSel(const V3& a, int k)
+{
+#if defined(__CUDA_ARCH__) && !defined(KDPT_LEAN_BRANCHY_AXIS)
+    float r;
+    asm("{ .reg .pred p1, p2;\n\t"
+        "setp.eq.s32 p1, %4, 1;\n\t"
+        "setp.eq.s32 p2, %4, 2;\n\t"
+        "selp.f32 %0, %2, %1, p1;\n\t"
+        "selp.f32 %0, %3, %0, p2; }" : "=&f"(r) : "f"(a.x), "f"(a.y), "f"(a.z), "r"(k));
+    return r;
+#else
+    return comp(a, k);
+#endif
+}
+
 struct HitCand { float t, nx, ny, nz; int mtl; };
 // interpolated normal, nudged point and its distance (pathtrace.cu:993-998) of a triangle glm accepted: the rare part of
 // the leaf loop, kept out of line so that the loop itself stays small
@@ -232,7 +249,7 @@ static unsigned long long g_leanRounds, g_leanEmpty, g_leanTris, g_leanSteps;
 struct PlaneCut { bool lowFirst, both; float tp; };
 KDPT_HD PlaneCut leanCut(const LeanState& S, int a, float split, float tmin, float tmax)
 {
-    const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+    const float oa = compSel(S.o, a), da = compSel(S.d, a), ia = compSel(S.inv, a);
     const bool below = oa < split || (oa == split && da <= 0.0f);
     const float tp = (split - oa) * ia;
     const bool nearOnly = da == 0.0f || tp <= 0.0f || tp >= tmax;
@@ -298,7 +315,7 @@ KDPT_HD void leanStep(const uint4 nd, LeanState& S, uint2* sStack, uint2* lStack
 {
     const int a = (int)(nd.w & 3u);
     const float split = __int_as_float((int)nd.x);
-    const float oa = comp(S.o, a), da = comp(S.d, a), ia = comp(S.inv, a);
+    const float oa = compSel(S.o, a), da = compSel(S.d, a), ia = compSel(S.inv, a);
     const bool below = oa < split || (oa == split && da <= 0.0f);
     const unsigned nearc = below ? nd.z : nd.y, farc = below ? nd.y : nd.z;
     const float tp = (split - oa) * ia;
