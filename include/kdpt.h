@@ -204,8 +204,8 @@ typedef struct {
                                    surface-area heuristic */
     int nodeForm;               /* how the exact modes' tree is laid out for their kernel. 1: one 16-byte record per node; 2: two
                                    levels per 32-byte record, small leaves named inline by their parents (half the dependent
-                                   loads of a descent; faster once the tree is several times the L2, slower below); 0: chosen by size
-                                   (two-level from 1 GB of device arrays on) */
+                                   loads of a descent; faster once the tree exceeds the L2, a little slower below); 0: chosen by size
+                                   (two-level from 256 MB of device arrays on) */
     int reserved[5];
 } kdpt_build_opts;
 int kdpt_create_opts(const kdpt_scene* scene, int device, const kdpt_build_opts* opts, kdpt_ctx** out);

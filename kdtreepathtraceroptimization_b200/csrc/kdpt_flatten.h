@@ -48,7 +48,7 @@ struct FlatTree {
     uint64_t bytes() const;
 };
 
-constexpr uint64_t kWideMinBytes = 1ull << 30;       // two-level records pay once the tree is several times the L2 (kdpt_lean.cuh)
+constexpr uint64_t kWideMinBytes = 256ull << 20;     // two-level records pay once the tree is beyond the L2 (kdpt_lean.cuh)
 
 struct FlattenOpts {
     int refineLeafMax = 8;      // leaves with more triangles than this are split further for the exact modes; 0 = off

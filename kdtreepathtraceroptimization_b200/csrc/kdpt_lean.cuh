@@ -48,9 +48,10 @@ constexpr int kLeanRing = 8;        // RESTART: entries in the ring
 //   kWideLeaf | 15 << 27 | xnodes index      (chunked or bigger leaves: their 16-byte leaf record)
 // One fetch decides two levels, so a descent is half as many dependent loads (dragon_5: 29 -> 12 per ray, leaf records included);
 // the far subtrees of both levels are cut by their planes at once and go to the stack as up to three (reference, exit
-// distance) entries, farthest first. Measured (profiles/r2_call20_empty_leaf_policies.txt): +6-10 % on the 10 M soup, +2 % on
-// the 1 M soup, +-1 % on the 1.6 M dragon, -2 to -5 % on trees that live in L1/L2 (dragon_5, bunny) where the extra plane
-// arithmetic costs more than the saved loads — so kdpt_create picks this form only for trees of 1 GB and more (kWideMinBytes).
+// distance) entries, farthest first. Measured (profiles/r2_call20_empty_leaf_policies.txt, r2_call23_axis_select.txt): +6-10 % on
+// the 10 M soup, +3 % on the 1.6 M dragon (with compSel below; +-1 % before it), -1 to -5 % on trees that live in L1/L2
+// (dragon_5, bunny) where the extra plane arithmetic costs more than the saved loads — so kdpt_create picks this form for trees
+// of 256 MB and more (kWideMinBytes).
 constexpr unsigned kWideLeaf = 0x80000000u;
 constexpr unsigned kWideIndexMask = (1u << 27) - 1u;
 constexpr int kWideStack = 48;      // 3 entries per record level, at most 16 record levels (buildWide refuses deeper trees)
