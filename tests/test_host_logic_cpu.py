@@ -303,3 +303,51 @@ def test_headless_cli_builds_and_fails_loudly_without_a_gpu():
     r = subprocess.run([exe, os.path.join(scenes, "cornell.txt"), os.path.join(scenes, "sphere_low_1.obj"), "--spp", "1"],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+def _check_contract(d, reference):
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and isinstance(d["config"].get("workload"), str)
+    assert "model" not in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    if reference:
+        assert d["impl"] == "reference" and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+        assert d["cpu_baseline"]["value"] == d["value"]
+    else:
+        assert d["gpu_launches"] > 0 and d["check"]["ok"] is True
+        r = d["roofline"]
+        for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert k in r, k
+        assert r["bound"] in ("hbm", "l2") and r["unit"] == "GB/s" and 0 < r["frac"] <= 1.0
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        c = d["clocks"]
+        assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and isinstance(c["reasons"], list)
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+
+
+def test_bench_line_contract():
+    """the JSON line of bench.py: the reference arm run live on its smallest workload (the reference's own host functions, no GPU, and
+    no libkdpt.so in that process), the product arm from the line the last GPU call of the round recorded"""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "sphere", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    _check_contract(json.loads(out.stdout.strip().splitlines()[-1]), reference=True)
+    lines = [l for l in open(os.path.join(ROOT, "profiles", "r2_bench_lines_final.txt")) if l.startswith("{")]
+    assert len(lines) >= 3
+    checked = 0
+    for l in lines:
+        d = json.loads(l)
+        if "1.6 M tris" in d["config"]["workload"]:         # the driver's commands (the 10 M soup line was taken without its CPU sample)
+            _check_contract(d, reference=d.get("impl") == "reference")
+            checked += 1
+    assert checked >= 3
+    assert "1.6 M tris" in json.loads(lines[-1])["config"]["workload"] and "1920x1080" in json.loads(lines[-1])["config"]["workload"]
