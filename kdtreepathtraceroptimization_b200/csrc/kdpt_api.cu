@@ -134,7 +134,8 @@ int kdpt_destroy(kdpt_ctx* ctx)
     for (auto& b : ctx->treeMem) b.release();
     DeviceBuffer* bufs[] = {&ctx->scene.geoms, &ctx->scene.materials, &ctx->scene.offsets, &ctx->scene.geomBounds, &ctx->rays, &ctx->tmin,
                             &ctx->hits, &ctx->counter, &ctx->image, &ctx->pathsA, &ctx->pathsB, &ctx->isects,
-                            &ctx->scanTmp, &ctx->keysTmp, &ctx->hist, &ctx->accum, &ctx->binTmp, &ctx->gqWork, &ctx->gqHit};
+                            &ctx->scanTmp, &ctx->keysTmp, &ctx->hist, &ctx->accum, &ctx->binTmp, &ctx->gqWork, &ctx->gqHit,
+                            &ctx->vizGeoms, &ctx->vizBounds};
     for (auto* b : bufs) b->release();
     cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev2, ctx->ev3};
     for (auto e : evs) if (e) cudaEventDestroy(e);
